@@ -1,0 +1,74 @@
+"""ctypes binding of ``libgnnome_b200.so`` (the C ABI declared in ``include/gnnome_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libgnnome_b200.so')
+
+_c_i32p = ctypes.c_void_p
+_c_f32p = ctypes.c_void_p
+
+
+class GnbGraph(ctypes.Structure):
+    """Mirror of ``gnb_graph_t``."""
+    _fields_ = [
+        ('num_nodes', ctypes.c_int64),
+        ('num_edges', ctypes.c_int64),
+        ('in_ptr', ctypes.c_void_p),
+        ('in_src', ctypes.c_void_p),
+        ('in_dst', ctypes.c_void_p),
+        ('in_eid', ctypes.c_void_p),
+        ('out_ptr', ctypes.c_void_p),
+        ('out_pos', ctypes.c_void_p),
+        ('out_dst', ctypes.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/gnnome_b200.h
+_P, _I, _L, _S = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+SIGNATURES = {
+    'gnb_abi_version': (_I, []),
+    'gnb_last_error': (ctypes.c_char_p, []),
+    'gnb_graph_stage_workspace': (_I, [_L, _L, ctypes.POINTER(_S)]),
+    'gnb_graph_stage': (_I, [_P, _P, ctypes.POINTER(GnbGraph), _P, _S, _P]),
+    'gnb_encode': (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'gnb_node_linear': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
+    'gnb_edge_chunk': (_I, [_I]),
+    'gnb_edge_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P]),
+    'gnb_node_update': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    'gnb_score_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'gnb_gather_rows': (_I, [_P, _P, _L, _I, _P, _P]),
+    'gnb_scatter_rows': (_I, [_P, _P, _L, _I, _P, _P]),
+}
+
+GNB_F_SYMMETRIC = 1
+GNB_F_RESIDUAL = 2
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise with a build hint if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'or `make -C {os.path.dirname(LIB_PATH)}` (there is no CPU fallback)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype, fn.argtypes = res, args
+    if lib.gnb_abi_version() != 1:
+        raise RuntimeError(f'libgnnome_b200 ABI {lib.gnb_abi_version()} != 1: rebuild')
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().gnb_last_error()
+        raise RuntimeError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')

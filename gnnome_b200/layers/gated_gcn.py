@@ -1,0 +1,135 @@
+"""(Sym)GatedGCN layers with the reference's constructor / parameter names, running on the
+sm_100a kernels.  Mirrors ``layers/gated_gcn_full.py`` of the reference (SymGatedGCN :8-142,
+GatedGCN :145-230): same ``nn.Linear`` / norm sub-modules (so ``state_dict`` keys and shapes are
+identical and ``weights/weights.pt`` loads strictly), same ``forward(g, h, e) -> (h, e)``.
+
+The arithmetic is NOT torch: one concatenated node projection, one fused edge pass over the
+dst-CSR, one reverse aggregation + node update over the src-CSR (see ``csrc/gnb_layers.cu``)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib, ops
+from ..graph import GraphIndex
+
+
+def _bn_affine(norm, device):
+    """Eval-mode BatchNorm1d as a per-channel affine, computed in fp64 (gated_gcn_full.py:37-38)."""
+    var = norm.running_var.detach().double()
+    scale = norm.weight.detach().double() / torch.sqrt(var + norm.eps)
+    shift = norm.bias.detach().double() - norm.running_mean.detach().double() * scale
+    return scale.to(device), shift.to(device)
+
+
+class _GatedGCNBase(nn.Module):
+    _symmetric = True
+
+    def __init__(self, in_channels, out_channels, normalization, dropout=None, residual=True):
+        super().__init__()
+        self.dropout = dropout if dropout else 0.0                 # gated_gcn_full.py:16-19
+        self.normalization = normalization
+        self.residual = residual
+        if in_channels != out_channels:                            # :24-25
+            self.residual = False
+        self.in_channels, self.out_channels = in_channels, out_channels
+        dtype = torch.float32
+        self.A_1 = nn.Linear(in_channels, out_channels, dtype=dtype)
+        self.A_2 = nn.Linear(in_channels, out_channels, dtype=dtype)
+        if self._symmetric:
+            self.A_3 = nn.Linear(in_channels, out_channels, dtype=dtype)
+        self.B_1 = nn.Linear(in_channels, out_channels, dtype=dtype)
+        self.B_2 = nn.Linear(in_channels, out_channels, dtype=dtype)
+        self.B_3 = nn.Linear(in_channels, out_channels, dtype=dtype)
+        if normalization == 'batch':
+            self.bn_h = nn.BatchNorm1d(out_channels, track_running_stats=True)
+            self.bn_e = nn.BatchNorm1d(out_channels, track_running_stats=True)
+        elif normalization == 'layer':
+            self.bn_h = nn.LayerNorm(out_channels)
+            self.bn_e = nn.LayerNorm(out_channels)
+
+    # -- parameter packing ---------------------------------------------------------------------
+    def _flags(self):
+        return (_lib.GNB_F_SYMMETRIC if self._symmetric else 0) | (_lib.GNB_F_RESIDUAL if self.residual else 0)
+
+    def _pack(self, device):
+        """Kernel-side views of the parameters: the concatenated k-major node projection with the
+        (B1, A2) rows interleaved per channel, the k-major edge projection, and the eval-mode norm
+        affines (b_B3 folded into the edge shift).  Recomputed per call (a few KB..MB)."""
+        H = self.out_channels
+        dev = dict(device=device, dtype=torch.float32)
+        w = lambda lin: lin.weight.detach().to(**dev)
+        b = lambda lin: lin.bias.detach().to(**dev)
+        blocks_w = [torch.stack((w(self.B_1), w(self.A_2)), dim=1).reshape(2 * H, -1), w(self.B_2)]
+        blocks_b = [torch.stack((b(self.B_1), b(self.A_2)), dim=1).reshape(2 * H), b(self.B_2)]
+        if self._symmetric:
+            blocks_w.append(w(self.A_3))
+            blocks_b.append(b(self.A_3))
+        blocks_w.append(w(self.A_1))
+        blocks_b.append(b(self.A_1))
+        Wn_t = torch.cat(blocks_w, dim=0).t().contiguous()           # [H_in][5H or 4H]
+        bn = torch.cat(blocks_b, dim=0).contiguous()
+        We_t = w(self.B_3).t().contiguous()                          # [H_in][H]
+        if self.normalization == 'batch':
+            se, te = _bn_affine(self.bn_e, device)
+            sh, th = _bn_affine(self.bn_h, device)
+        else:
+            raise NotImplementedError(f"normalization={self.normalization!r}: only eval-mode 'batch' runs on the "
+                                      f"CUDA path so far")
+        te = te + se * self.B_3.bias.detach().double().to(device)
+        f32 = lambda t: t.to(torch.float32).contiguous()
+        return dict(Wn_t=Wn_t, bn=bn, We_t=We_t, scale_e=f32(se), shift_e=f32(te), scale_h=f32(sh), shift_h=f32(th))
+
+    # -- position-order fast path (what the processor / model use) -----------------------------
+    def forward_positions(self, gi: GraphIndex, h, e_pos, ws=None):
+        """One layer with edge rows already in dst-sorted position order.  ``e_pos`` is updated IN
+        PLACE (legal: e'_p depends only on e_p, h[src_p], h[dst_p]) and returned."""
+        if self.training:
+            raise NotImplementedError('training mode runs through gnnome_b200.autograd (not built yet)')
+        if self.in_channels != self.out_channels:
+            raise NotImplementedError('in_channels != out_channels is not supported by the CUDA path')
+        H = self.out_channels
+        dev = h.device
+        pk = self._pack(dev)
+        ws = ws if ws is not None else {}
+        n_blocks = 5 if self._symmetric else 4
+        P = ws.get('P')
+        if P is None or P.shape != (gi.N, n_blocks * H):
+            P = ws['P'] = torch.empty((gi.N, n_blocks * H), dtype=torch.float32, device=dev)
+        Fb = ws.get('F')
+        if Fb is None or Fb.shape != (gi.N, H):
+            Fb = ws['F'] = torch.empty((gi.N, H), dtype=torch.float32, device=dev)
+        carry = ws.get('carry')
+        if carry is None or carry.shape != (gi.num_chunks(H), 4, H):
+            carry = ws['carry'] = torch.empty((gi.num_chunks(H), 4, H), dtype=torch.float32, device=dev)
+        h_out = ws.pop('h_spare', None)
+        if h_out is None or h_out.shape != h.shape or h_out.data_ptr() == h.data_ptr():
+            h_out = torch.empty_like(h)
+        flags = self._flags()
+        ops.node_linear(h, pk['Wn_t'], pk['bn'], out=P)
+        ops.edge_forward(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry, flags)
+        ops.node_update(gi, H, P, e_pos, Fb, carry, h, pk['scale_h'], pk['shift_h'], h_out, flags)
+        ws['h_spare'] = h  # ping-pong: the caller no longer needs the input h
+        return h_out, e_pos
+
+    # -- reference-compatible layer API ------------------------------------------------------------
+    def forward(self, g, h, e):
+        """``h, e = conv(g, h, e)`` with ``e`` in the graph's edge-id order (gated_gcn_full.py:82)."""
+        gi = GraphIndex.from_graph(g)
+        out_dev = h.device
+        h_d = h.detach().to(device=gi.device, dtype=torch.float32).contiguous()
+        e_d = e.detach().to(device=gi.device, dtype=torch.float32).contiguous()
+        e_pos = ops.gather_rows(e_d, gi.in_eid[:gi.E])
+        h_new, e_pos = self.forward_positions(gi, h_d.clone(), e_pos)
+        e_new = ops.scatter_rows(e_pos, gi.in_eid[:gi.E])
+        h_new = F.dropout(h_new, self.dropout, training=self.training)  # :139
+        return h_new.to(out_dev), e_new.to(out_dev)
+
+
+class SymGatedGCN(_GatedGCNBase):
+    """reference layers/gated_gcn_full.py:8-142"""
+    _symmetric = True
+
+
+class GatedGCN(_GatedGCNBase):
+    """reference layers/gated_gcn_full.py:145-230 (no A_3, no reverse aggregation)"""
+    _symmetric = False

@@ -1,0 +1,38 @@
+"""Edge-score MLP -- reference ``layers/score_predictor.py:5-24``."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..graph import GraphIndex
+
+
+class ScorePredictor(nn.Module):
+    def __init__(self, in_features, hidden_edge_scores):
+        super().__init__()
+        self.W1 = nn.Linear(3 * in_features, hidden_edge_scores)
+        self.W2 = nn.Linear(hidden_edge_scores, 32)
+        self.W3 = nn.Linear(32, 1)
+        self.in_features, self.hidden_edge_scores = in_features, hidden_edge_scores
+
+    def forward_positions(self, gi: GraphIndex, x, e_pos):
+        """Scores in ORIGINAL edge-id order, shape (E, 1), from position-ordered edge rows."""
+        H, hs = self.in_features, self.hidden_edge_scores
+        dev = dict(device=x.device, dtype=torch.float32)
+        W1 = self.W1.weight.detach().to(**dev)                      # [hs][3H] = [W1s | W1d | W1e]
+        Ws_t = torch.cat((W1[:, :H], W1[:, H:2 * H]), dim=0).t().contiguous()   # [H][2hs]
+        bias = torch.cat((torch.zeros(hs, **dev), self.W1.bias.detach().to(**dev)))
+        W1e_t = W1[:, 2 * H:].t().contiguous()                      # [H][hs]
+        S = ops.node_linear(x, Ws_t, bias)
+        scores = torch.empty((gi.E, 1), **dev)
+        ops.score_forward(gi, H, hs, S, W1e_t, self.W2.weight.detach().to(**dev).contiguous(),
+                          self.W2.bias.detach().to(**dev), self.W3.weight.detach().to(**dev).reshape(-1).contiguous(),
+                          self.W3.bias.detach().to(**dev), e_pos, scores)
+        return scores
+
+    def forward(self, graph, x, e):
+        gi = GraphIndex.from_graph(graph)
+        out_dev = x.device
+        x_d = x.detach().to(device=gi.device, dtype=torch.float32).contiguous()
+        e_d = e.detach().to(device=gi.device, dtype=torch.float32).contiguous()
+        e_pos = ops.gather_rows(e_d, gi.in_eid[:gi.E])
+        return self.forward_positions(gi, x_d, e_pos).to(out_dev)

@@ -1,0 +1,127 @@
+/* gnnome_b200 -- C ABI of the B200-native GatedGCN + edge-score path.
+ *
+ * The reference (lbcb-sci/GNNome) is pure Python and has no FFI layer; its "operator API" for this
+ * path is the nn.Module surface of layers/ and models/ (SURVEY.md section 8b).  The entry points
+ * below are what a ctypes binding inside those modules calls; each cites the reference lines whose
+ * arithmetic it replaces.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch); the library allocates nothing
+ *    and keeps no state between calls.  All launches go to the caller's stream; no implicit sync.
+ *  - return 0 on success, a cudaError_t (> 0) or a negative GNB_E_* code otherwise; the message is
+ *    in gnb_last_error() (thread local).  Nothing aborts or throws across the ABI.
+ *  - dense matrices are row-major fp32.  "k-major" weight = the transpose of nn.Linear.weight,
+ *    i.e. Wt[k][n] = weight[n][k], so that consecutive outputs n are contiguous.
+ *  - edge state lives in DST-SORTED order (position p), see gnb_graph_t; gnb_gather_rows converts.
+ *  - H (hidden_features) must be one of 32, 64, 128, 256.
+ */
+#ifndef GNNOME_B200_H
+#define GNNOME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNB_ABI_VERSION 1
+
+#define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
+#define GNB_E_WORKSPACE (-2)  /* workspace too small */
+#define GNB_E_ARCH      (-3)  /* device is not sm_100 */
+
+/* flags for gnb_edge_forward / gnb_node_update */
+#define GNB_F_SYMMETRIC 1  /* SymGatedGCN: also aggregate over out-edges with A3h (gated_gcn_full.py:117-127) */
+#define GNB_F_RESIDUAL  2  /* in_channels == out_channels (gated_gcn_full.py:24-25,108,136) */
+
+/* Staged graph: the two CSR views the kernels walk.  Replaces what DGL builds behind
+ * g.apply_edges / g.update_all / dgl.reverse (gated_gcn_full.py:99,104,112-113,117,125-126).
+ * Position p in [0,E) enumerates edges sorted by (dst, original id); q enumerates them sorted by
+ * (src, p).  All arrays int32, caller-allocated, filled by gnb_graph_stage. */
+typedef struct gnb_graph {
+  int64_t num_nodes;
+  int64_t num_edges;
+  int32_t* in_ptr;   /* [N+1] in-edges of node i are positions in_ptr[i] .. in_ptr[i+1]        */
+  int32_t* in_src;   /* [E]   source node of the edge at position p                              */
+  int32_t* in_dst;   /* [E]   destination node of the edge at position p (non-decreasing)        */
+  int32_t* in_eid;   /* [E]   original (DGL) edge id of the edge at position p                   */
+  int32_t* out_ptr;  /* [N+1] out-edges of node i are q in out_ptr[i] .. out_ptr[i+1]            */
+  int32_t* out_pos;  /* [E]   position p of the q-th edge in src-sorted order                    */
+  int32_t* out_dst;  /* [E]   destination node of that edge                                      */
+} gnb_graph_t;
+
+int gnb_abi_version(void);
+const char* gnb_last_error(void);
+
+/* Bytes of scratch gnb_graph_stage needs for (E, N). */
+int gnb_graph_stage_workspace(int64_t num_edges, int64_t num_nodes, size_t* bytes);
+
+/* Build both CSR views from the COO edge list (src[k], dst[k]) in original edge-id order.
+ * g->num_nodes / num_edges and the seven array pointers must be set by the caller. */
+int gnb_graph_stage(const int32_t* src, const int32_t* dst, gnb_graph_t* g,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[r][:] = W2 * relu(W1 * in[idx ? idx[r] : r][:] + b1) + b2
+ * The two-layer encoders: models/full_graph.py:26-27, layers/node_encoder.py:28-33,
+ * layers/edge_encoder.py:27-32.  W1 is [hid][in_f] (nn.Linear layout), W2t is k-major [hid][H]. */
+int gnb_encode(const float* in, const int32_t* idx, int64_t rows, int in_f, int hid, int H,
+               const float* W1, const float* b1, const float* W2t, const float* b2,
+               float* out, void* stream);
+
+/* out[r][0:M] = A[r][0:K] * Wt + bias, Wt k-major [K][M].  The node-side nn.Linear calls
+ * A_1,A_2,A_3,B_1,B_2 (gated_gcn_full.py:91-96) as ONE product with the concatenated weight, and
+ * the node half of ScorePredictor.W1 (score_predictor.py:13-14).  K % 16 == 0, M % 4 == 0. */
+int gnb_node_linear(const float* A, int64_t rows, int K, const float* Wt, const float* bias, int M,
+                    float* out, int64_t ld_out, void* stream);
+
+/* Number of consecutive edge positions one aggregation chunk covers (carry granularity). */
+int gnb_edge_chunk(int H);
+
+/* Fused edge pass of one (Sym)GatedGCN layer over the dst-CSR (gated_gcn_full.py:97,104-114):
+ *   z_p   = P[src_p][B1h] + P[dst_p][B2h] + e_p * We_t
+ *   e'_p  = relu(z_p * scale_e + shift_e) (+ e_p if GNB_F_RESIDUAL)       -> written over e in place
+ *   s_p   = sigmoid(e'_p)
+ *   F_i   = sum_{p: dst_p = i} s_p * P[src_p][A2h] / (sum_p s_p + 1e-6)
+ * P is the node table [N][ldP] written by gnb_node_linear with column blocks
+ *   [0,2H): (B1h[c], A2h[c]) interleaved per channel c | [2H,3H): B2h | [3H,4H): A3h | [4H,5H): A1h
+ * (non-symmetric layers have no A3h block: [3H,4H) is A1h).  b_B3 is folded into shift_e by the
+ * caller (shift_e = bn shift + scale * b_B3); in eval mode scale/shift are the BatchNorm affine.
+ * Segments that straddle a chunk boundary leave partial sums in carry[chunk][4][H]
+ * (head num, head den, tail num, tail den); gnb_node_update resolves them, so F alone is only
+ * meaningful together with carry.  carry has ceil(E / gnb_edge_chunk(H)) entries. */
+int gnb_edge_forward(const gnb_graph_t* g, int H, const float* P, int64_t ldP,
+                     const float* We_t, const float* scale_e, const float* shift_e,
+                     float* e, float* F, float* carry, int flags, void* stream);
+
+/* Reverse aggregation over the src-CSR fused with the node update (gated_gcn_full.py:124-137):
+ *   Bk_i = sum_{q: src_q = i} sigmoid(e'_q) * P[dst_q][A3h] / (sum_q sigmoid(e'_q) + 1e-6)   (symmetric only)
+ *   h'_i = relu((P[i][A1h] + F_i + Bk_i) * scale_h + shift_h) (+ h_i if GNB_F_RESIDUAL)
+ * Dropout (gated_gcn_full.py:139) is left to the caller (torch RNG semantics). */
+int gnb_node_update(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const float* e,
+                    const float* F, const float* carry, const float* h_in,
+                    const float* scale_h, const float* shift_h, float* h_out, int flags,
+                    void* stream);
+
+/* ScorePredictor (score_predictor.py:12-24) with W1 = [W1s | W1d | W1e] split so that the node
+ * halves are projected once per node:  S[n] = [x_n * W1s^T | x_n * W1d^T + b1]  ([N][2*hs], from
+ * gnb_node_linear), then per edge
+ *   score = W3 * relu(W2 * relu(S[src][0:hs] + S[dst][hs:2hs] + e_p * W1e_t) + b2) + b3
+ * written to scores[in_eid[p]] (original edge order, [E] == the reference's (E,1)).
+ * hs must be 32, 64 or 128; W2 is [32][hs] (nn.Linear layout), W3 is [32]. */
+int gnb_score_forward(const gnb_graph_t* g, int H, int hs, const float* S, const float* W1e_t,
+                      const float* W2, const float* b2, const float* W3, const float* b3,
+                      const float* e, float* scores, void* stream);
+
+/* out[r][0:W] = in[idx[r]][0:W]  (W % 4 == 0).  Moves edge rows between original order and
+ * position order for the layer-level API. */
+int gnb_gather_rows(const float* in, const int32_t* idx, int64_t rows, int W, float* out,
+                    void* stream);
+/* out[idx[r]][0:W] = in[r][0:W] */
+int gnb_scatter_rows(const float* in, const int32_t* idx, int64_t rows, int W, float* out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNOME_B200_H */
