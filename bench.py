@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- edges/s of the GatedGCN forward + edge-score pass (BASELINE.json metric).
+
+One "step" = one ``model(graph, x, e)`` pass (encoders -> 8 SymGatedGCN layers -> ScorePredictor,
+eval mode) over one synthetic power-law assembly graph of the shape BASELINE.json names.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|...] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU): the graph is partitioned by destination-node
+range, every rank runs the same kernels on its shard and exchanges halo rows over NCCL
+(gnnome_b200.partition); timing is max-over-ranks, value = global edges / that time.
+
+Keys of the JSON line (rank 0 prints exactly one):
+  value      edges/s with the staged graph, x and e already resident in HBM (CUDA events)
+  e2e        edges/s through the public model call with PINNED HOST src/dst/x/e: H2D copies, graph
+             staging (two device radix sorts), forward, D2H of the (E,1) scores -- all timed
+  roofline   the dominant kernel (gnb_edge_forward): its algorithmic bytes / its mean launch time
+             measured with CUDA events inside the timed region, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (restatement of the reference's algorithm) on a bounded sample of
+             the same workload, all host threads, plus the GPU-vs-oracle parity on that sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, E, H, L, description)
+    'cfg3': (10_000_000, 60_000_000, 256, 8, 'synthetic power-law assembly graph 10M nodes / 60M edges, hidden=256, L=8'),
+    'cfg2': (1_000_000, 6_000_000, 128, 8, 'synthetic power-law assembly graph 1M nodes / 6M edges, hidden=128, L=8'),
+    'cfg2s': (1_000_000, 6_000_000, 64, 8, 'synthetic 1M nodes / 6M edges, hidden=64 (shipped-model width), L=8'),
+    'small': (100_000, 600_000, 256, 8, 'synthetic 100k nodes / 600k edges, hidden=256, L=8 (debug size)'),
+}
+CPU_SAMPLE = (40_000, 240_000)      # bounded sample of the workload for the CPU arm (same H, L, generator)
+HIDDEN_NE, HIDDEN_SCORES = 16, 64   # configs/hyperparameters.py:24-25 of the reference
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def dist_env():
+    return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+
+
+def make_model(H, L, device=None):
+    import gnnome_b200
+    torch.manual_seed(0)
+    model = gnnome_b200.models.SymGatedGCNModel(2, 2, H, HIDDEN_NE, L, HIDDEN_SCORES, 'batch', dropout=None)
+    model.eval()
+    return model.to(device) if device is not None else model
+
+
+def make_inputs(n, m, seed=0):
+    from gnnome_b200 import synth
+    t0 = time.time()
+    src, dst = synth.make_assembly_graph(n, m, seed=seed)
+    x, e = synth.make_features(src, dst, n, seed=seed)
+    log(f'[bench] generated graph N={n} E={m} in {time.time() - t0:.1f}s')
+    return tuple(torch.from_numpy(a) for a in (src, dst, x, e))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], 0.0, set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': smax, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except (OSError, KeyError, ValueError):
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def edge_kernel_bytes(n_nodes, n_edges, H):
+    """Algorithmic (compulsory) bytes of ONE gnb_edge_forward launch, fp32 state, int32 indices:
+    read e + write e' (2*E*H*4), read src/dst (8E), read the B1h/A2h/B2h node rows once each and
+    write F (4*N*H*4).  See DESIGN.md section 4."""
+    return n_edges * (2 * H * 4 + 8) + n_nodes * 4 * H * 4
+
+
+def forward_bytes(n_nodes, n_edges, H, L):
+    """B_fwd = (2L+2)(E*H*s_e + N*H*s_h) + (8L+20)E + 8N with fp32 state."""
+    return (2 * L + 2) * (n_edges * H * 4 + n_nodes * H * 4) + (8 * L + 20) * n_edges + 8 * n_nodes
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restatement of the reference's algorithm) on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_run(state_dict, H, L, steps, warmup, sample=CPU_SAMPLE, seed=1):
+    from oracle import restatement as R   # allowed here: cpu_baseline / --impl reference legs only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n, m = sample
+    src, dst, x, e = make_inputs(n, m, seed=seed)
+    times, out = [], None
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = R.model_forward(state_dict, src, dst, n, x, e, faithful=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return dict(n=n, m=m, times=times, out=out, inputs=(src, dst, x, e), cores=cores)
+
+
+def run_reference_arm(args, wl):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    n, m, H, L, desc = wl
+    model = make_model(H, L)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    r = cpu_oracle_run(sd, H, L, steps=args.steps, warmup=min(args.warmup, 1))
+    t = float(np.mean(r['times']))
+    value = r['m'] / t
+    sample = (f'N={r["n"]} E={r["m"]} (same generator/H={H}/L={L}; the full workload needs ~14 KB/edge of host RAM '
+              f'on the reference path)')
+    line = {
+        'impl': 'reference', 'metric': 'edges/s', 'value': value, 'unit': 'edges/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': t * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'N': n, 'E': m, 'H': H, 'L': L, 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'edges/s', 'cores': r['cores'], 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, wl):
+    import gnnome_b200
+    from gnnome_b200 import ops, _lib
+    rank, local_rank, world = dist_env()
+    n, m, H, L, desc = wl
+    if world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torchrun')
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    _lib.load()
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+
+    model = make_model(H, L, device)
+    src, dst, x, e = make_inputs(n, m, seed=0)
+
+    if world > 1:
+        from gnnome_b200 import partition
+        runner = partition.ShardedForward(model, src, dst, n, x, e, rank, world, device)
+    else:
+        runner = None
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement ---------------------------------------------------------
+    if runner is None:
+        gi = gnnome_b200.GraphIndex(src, dst, n, device)
+        x_d, e_d = x.to(device), e.to(device)
+        step = lambda: model(gi, x_d, e_d)
+    else:
+        step = runner.step
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = step()
+        barrier()
+        ops.LaunchLog.reset(enabled=True, timing=True)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = ops.LaunchLog.total()
+    ktimes = ops.LaunchLog.times_ms()
+    ops.LaunchLog.reset(enabled=False)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = m / (ms * 1e-3)
+    breakdown = {k: {'launches_per_step': len(v) / args.steps, 'ms_per_step': float(np.sum(v)) / args.steps}
+                 for k, v in sorted(ktimes.items())}
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    peak, peak_src = measured_peak()
+    ek = ktimes.get('gnb_edge_forward', [])
+    roofline = None
+    if ek:
+        n_loc, m_loc = (runner.local_sizes() if runner is not None else (n, m))
+        kb = edge_kernel_bytes(n_loc, m_loc, H)
+        achieved = kb / (float(np.mean(ek)) * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'gnb_edge_forward', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': kb, 'ms_per_launch': float(np.mean(ek)),
+                    'whole_forward_frac': forward_bytes(n, m, H, L) / (ms * 1e-3) / 1e9 / peak / world}
+
+    # ---- end-to-end through the public call with pinned host buffers ---------------------------
+    e2e = None
+    if runner is None:
+        hs, hd, hx, he = (t.pin_memory() for t in (src, dst, x, e))
+        e2e_steps = max(1, min(args.steps, 3))
+        host_out = torch.empty((m, 1), dtype=torch.float32).pin_memory()
+        with torch.no_grad():
+            def e2e_step():
+                o = model((hs.to(device, non_blocking=True), hd.to(device, non_blocking=True), n),
+                          hx.to(device, non_blocking=True), he.to(device, non_blocking=True))
+                host_out.copy_(o, non_blocking=True)
+            e2e_step()
+            barrier()
+            ev0.record()
+            for _ in range(e2e_steps):
+                e2e_step()
+            ev1.record()
+            barrier()
+        e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
+        e2e = {'value': m / (e2e_ms * 1e-3), 'unit': 'edges/s', 'ms_per_step': e2e_ms, 'steps': e2e_steps,
+               'h2d_bytes_per_step': int(sum(t.numel() * t.element_size() for t in (hs, hd, hx, he))),
+               'd2h_bytes_per_step': int(host_out.numel() * 4),
+               'includes': 'H2D of src/dst/x/e, graph staging (2 radix sorts), forward, D2H of scores'}
+    else:
+        e2e = runner.e2e(args, barrier)
+
+    if rank != 0:
+        return
+    # ---- CPU baseline + parity on the bounded sample (rank 0, N=1 only) ------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        del out
+        torch.cuda.empty_cache()
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        r = cpu_oracle_run(sd, H, L, steps=1, warmup=0)
+        s_src, s_dst, s_x, s_e = r['inputs']
+        with torch.no_grad():
+            ours = model((s_src, s_dst, r['n']), s_x, s_e)
+        perr = (torch.sigmoid(ours.double().cpu()) - torch.sigmoid(r['out'].double())).abs().max().item()
+        cpu = {'value': r['m'] / r['times'][0], 'unit': 'edges/s', 'cores': r['cores'], 'kind': 'port',
+               'sample': f'N={r["n"]} E={r["m"]} H={H} L={L}, same generator, 1 pass ({r["times"][0]:.1f}s); torch '
+                         f'{torch.__version__} CPU threads={r["cores"]}',
+               'parity_max_prob_err_on_sample': perr}
+
+    line = {
+        'metric': 'edges/s', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if world > 1 else 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'N': n, 'E': m, 'H': H, 'L': L, 'model': 'SymGatedGCNModel eval, seed-0 init',
+                   'graph': 'make_assembly_graph(seed=0, band=64, alpha=2.2, p_long=0.01)',
+                   'l2': 'inputs (>= 1 GB of edge state per layer) exceed the 126 MB L2; no flush needed',
+                   'parallelism': f'dst-range x{world}' if world > 1 else 'single GPU'},
+        'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
+        'kernels': breakdown,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='gnnome_b200', choices=['gnnome_b200', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference_arm(args, wl)
+    else:
+        run_gpu_arm(args, wl)
+
+
+if __name__ == '__main__':
+    main()

@@ -8,6 +8,51 @@ from . import _lib
 from .graph import GraphIndex, current_stream_ptr
 
 
+class LaunchLog:
+    """Opt-in accounting of the library's kernel launches (used by bench.py): counts every C-ABI
+    compute call and, when ``timing`` is on, brackets it with CUDA events on the launching stream
+    so that per-kernel device time can be read back after a synchronize."""
+    enabled = False
+    timing = False
+    counts = {}
+    events = {}
+
+    @classmethod
+    def reset(cls, enabled=True, timing=False):
+        cls.enabled, cls.timing, cls.counts, cls.events = enabled, timing, {}, {}
+
+    @classmethod
+    def total(cls):
+        return sum(cls.counts.values())
+
+    @classmethod
+    def times_ms(cls):
+        """name -> list of per-launch milliseconds (call after torch.cuda.synchronize())."""
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in cls.events.items()}
+
+
+class _logged:
+    def __init__(self, name, device, launches=1):
+        self.name, self.device, self.launches = name, device, launches
+
+    def __enter__(self):
+        self.dev_ctx = torch.cuda.device(self.device)
+        self.dev_ctx.__enter__()
+        if LaunchLog.enabled:
+            LaunchLog.counts[self.name] = LaunchLog.counts.get(self.name, 0) + self.launches
+            if LaunchLog.timing:
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.start.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if LaunchLog.enabled and LaunchLog.timing and exc[0] is None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(torch.cuda.current_stream(self.device))
+            LaunchLog.events.setdefault(self.name, []).append((self.start, end))
+        return self.dev_ctx.__exit__(*exc)
+
+
 def _f32(t, name):
     if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
         raise ValueError(f'{name} must be a contiguous float32 CUDA tensor (got {t.dtype}, {t.device})')
@@ -25,7 +70,7 @@ def encode(x, idx, W1, b1, W2t, b2, rows, out=None):
     H = W2t.shape[1]
     if out is None:
         out = torch.empty((rows, H), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _logged('gnb_encode', x.device):
         _lib.check(lib.gnb_encode(_f32(x, 'x'), _opt(idx), rows, in_f, hid, H, _f32(W1, 'W1'), _f32(b1, 'b1'),
                                   _f32(W2t, 'W2t'), _f32(b2, 'b2'), _f32(out, 'out'),
                                   current_stream_ptr(x.device)), 'gnb_encode')
@@ -39,7 +84,7 @@ def node_linear(a, Wt, bias, out=None):
     M = Wt.shape[1]
     if out is None:
         out = torch.empty((rows, M), dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with _logged('gnb_node_linear', a.device):
         _lib.check(lib.gnb_node_linear(_f32(a, 'a'), rows, K, _f32(Wt, 'Wt'), _f32(bias, 'bias'), M,
                                        _f32(out, 'out'), out.stride(0), current_stream_ptr(a.device)),
                    'gnb_node_linear')
@@ -48,7 +93,7 @@ def node_linear(a, Wt, bias, out=None):
 
 def edge_forward(gi: GraphIndex, H, P, We_t, scale_e, shift_e, e, F, carry, flags):
     lib = _lib.load()
-    with torch.cuda.device(e.device):
+    with _logged('gnb_edge_forward', e.device):
         _lib.check(lib.gnb_edge_forward(gi.ref(), H, _f32(P, 'P'), P.stride(0), _f32(We_t, 'We_t'),
                                         _f32(scale_e, 'scale_e'), _f32(shift_e, 'shift_e'), _f32(e, 'e'),
                                         _f32(F, 'F'), _f32(carry, 'carry'), flags,
@@ -57,7 +102,7 @@ def edge_forward(gi: GraphIndex, H, P, We_t, scale_e, shift_e, e, F, carry, flag
 
 def node_update(gi: GraphIndex, H, P, e, F, carry, h_in, scale_h, shift_h, h_out, flags):
     lib = _lib.load()
-    with torch.cuda.device(h_in.device):
+    with _logged('gnb_node_update', h_in.device):
         _lib.check(lib.gnb_node_update(gi.ref(), H, _f32(P, 'P'), P.stride(0), _f32(e, 'e'), _f32(F, 'F'),
                                        _f32(carry, 'carry'), _f32(h_in, 'h_in'), _f32(scale_h, 'scale_h'),
                                        _f32(shift_h, 'shift_h'), _f32(h_out, 'h_out'), flags,
@@ -66,7 +111,7 @@ def node_update(gi: GraphIndex, H, P, e, F, carry, h_in, scale_h, shift_h, h_out
 
 def score_forward(gi: GraphIndex, H, hs, S, W1e_t, W2, b2, W3, b3, e, scores):
     lib = _lib.load()
-    with torch.cuda.device(e.device):
+    with _logged('gnb_score_forward', e.device):
         _lib.check(lib.gnb_score_forward(gi.ref(), H, hs, _f32(S, 'S'), _f32(W1e_t, 'W1e_t'), _f32(W2, 'W2'),
                                          _f32(b2, 'b2'), _f32(W3, 'W3'), _f32(b3, 'b3'), _f32(e, 'e'),
                                          _f32(scores, 'scores'), current_stream_ptr(e.device)),
@@ -78,7 +123,7 @@ def gather_rows(x, idx, out=None):
     rows, W = idx.numel(), x.shape[1]
     if out is None:
         out = torch.empty((rows, W), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _logged('gnb_gather_rows', x.device):
         _lib.check(lib.gnb_gather_rows(_f32(x, 'x'), idx.data_ptr(), rows, W, _f32(out, 'out'),
                                        current_stream_ptr(x.device)), 'gnb_gather_rows')
     return out
@@ -89,7 +134,7 @@ def scatter_rows(x, idx, out=None):
     rows, W = idx.numel(), x.shape[1]
     if out is None:
         out = torch.empty((rows, W), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _logged('gnb_scatter_rows', x.device):
         _lib.check(lib.gnb_scatter_rows(_f32(x, 'x'), idx.data_ptr(), rows, W, _f32(out, 'out'),
                                         current_stream_ptr(x.device)), 'gnb_scatter_rows')
     return out
