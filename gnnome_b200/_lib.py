@@ -35,6 +35,9 @@ SIGNATURES = {
     'gnb_graph_stage': (_I, [_P, _P, ctypes.POINTER(GnbGraph), _P, _S, _P]),
     'gnb_encode': (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'gnb_node_linear': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
+    'gnb_packed_linear_bytes': (_S, [_I, _I]),
+    'gnb_pack_linear_tc': (_I, [_P, _I, _I, _P, _P]),
+    'gnb_node_linear_tc': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
     'gnb_edge_chunk': (_I, [_I]),
     'gnb_edge_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P]),
     'gnb_node_update': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P]),

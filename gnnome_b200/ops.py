@@ -91,6 +91,30 @@ def node_linear(a, Wt, bias, out=None):
     return out
 
 
+def pack_linear_tc(W):
+    """nn.Linear weight [M][K] -> packed fp16 (hi, lo) blocks for the tensor-core kernels."""
+    lib = _lib.load()
+    M, K = W.shape
+    out = torch.empty(lib.gnb_packed_linear_bytes(M, K), dtype=torch.uint8, device=W.device)
+    with _logged('gnb_pack_linear_tc', W.device):
+        _lib.check(lib.gnb_pack_linear_tc(_f32(W, 'W'), M, K, out.data_ptr(), current_stream_ptr(W.device)),
+                   'gnb_pack_linear_tc')
+    return out
+
+
+def node_linear_tc(a, Wp, bias, M, out=None):
+    """out = a @ W.T + bias on the tensor cores; Wp = pack_linear_tc(W[M][K])."""
+    lib = _lib.load()
+    rows, K = a.shape
+    if out is None:
+        out = torch.empty((rows, M), dtype=torch.float32, device=a.device)
+    with _logged('gnb_node_linear_tc', a.device):
+        _lib.check(lib.gnb_node_linear_tc(_f32(a, 'a'), rows, K, Wp.data_ptr(), _f32(bias, 'bias'), M,
+                                          _f32(out, 'out'), out.stride(0), current_stream_ptr(a.device)),
+                   'gnb_node_linear_tc')
+    return out
+
+
 def edge_forward(gi: GraphIndex, H, P, We_t, scale_e, shift_e, e, F, carry, flags):
     lib = _lib.load()
     with _logged('gnb_edge_forward', e.device):

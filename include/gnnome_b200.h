@@ -75,6 +75,22 @@ int gnb_encode(const float* in, const int32_t* idx, int64_t rows, int in_f, int 
 int gnb_node_linear(const float* A, int64_t rows, int K, const float* Wt, const float* bias, int M,
                     float* out, int64_t ld_out, void* stream);
 
+/* ---- tensor-core (tcgen05) variants ---------------------------------------------------------------
+ * The dense products run on the 5th-generation tensor cores with fp32 operands split on the fly into
+ * fp16 (hi, lo) pairs and three MMAs accumulated in fp32 (TMEM): accuracy indistinguishable from the
+ * fp32 FFMA kernels above.  Weights are pre-split once per parameter update. */
+
+/* Bytes of the packed image of an [M][K] nn.Linear weight (ceil(M/128) blocks x (hi, lo) x 128 x K fp16). */
+size_t gnb_packed_linear_bytes(int M, int K);
+
+/* W[M][K] (nn.Linear layout, fp32) -> packed fp16 (hi, lo) blocks at Wp (16-byte aligned). K % 16 == 0. */
+int gnb_pack_linear_tc(const float* W, int M, int K, void* Wp, void* stream);
+
+/* Same contract as gnb_node_linear with the weight given as gnb_pack_linear_tc(W[M][K]) output.
+ * K in {32, 64, 128, 256}; X 32-byte aligned. */
+int gnb_node_linear_tc(const float* X, int64_t rows, int K, const void* Wp, const float* bias, int M,
+                       float* out, int64_t ld_out, void* stream);
+
 /* Number of consecutive edge positions one aggregation chunk covers (carry granularity). */
 int gnb_edge_chunk(int H);
 
