@@ -251,13 +251,14 @@ def run_gpu_arm(args, wl):
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     peak, peak_src = measured_peak()
-    ek = ktimes.get('gnb_edge_forward', [])
+    ek_name = 'gnb_edge_forward_tc' if 'gnb_edge_forward_tc' in ktimes else 'gnb_edge_forward'
+    ek = ktimes.get(ek_name, [])
     roofline = None
     if ek:
         n_loc, m_loc = (runner.local_sizes() if runner is not None else (n, m))
         kb = edge_kernel_bytes(n_loc, m_loc, H)
         achieved = kb / (float(np.mean(ek)) * 1e-3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'gnb_edge_forward', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        roofline = {'bound': 'hbm', 'kernel': ek_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': kb, 'ms_per_launch': float(np.mean(ek)),
                     'whole_forward_frac': forward_bytes(n, m, H, L) / (ms * 1e-3) / 1e9 / peak / world}
@@ -309,7 +310,7 @@ def run_gpu_arm(args, wl):
     line = {
         'metric': 'edges/s', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if world > 1 else 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': 'f32 state, fp16x2-split tensor-core products with f32 accumulate', 'data': 'synthetic',
         'config': {'workload': desc, 'N': n, 'E': m, 'H': H, 'L': L, 'model': 'SymGatedGCNModel eval, seed-0 init',
                    'graph': 'make_assembly_graph(seed=0, band=64, alpha=2.2, p_long=0.01)',
                    'l2': 'inputs (>= 1 GB of edge state per layer) exceed the 126 MB L2; no flush needed',

@@ -40,12 +40,16 @@ SIGNATURES = {
     'gnb_node_linear_tc': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
     'gnb_edge_chunk': (_I, [_I]),
     'gnb_edge_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P]),
-    'gnb_node_update': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    'gnb_node_update': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    'gnb_edge_chunk_tc': (_I, [_I]),
+    'gnb_edge_tile_tc': (_I, [_I]),
+    'gnb_edge_forward_tc': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     'gnb_score_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'gnb_gather_rows': (_I, [_P, _P, _L, _I, _P, _P]),
     'gnb_scatter_rows': (_I, [_P, _P, _L, _I, _P, _P]),
 }
 
+ABI_VERSION = 2
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 
@@ -65,8 +69,8 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype, fn.argtypes = res, args
-    if lib.gnb_abi_version() != 1:
-        raise RuntimeError(f'libgnnome_b200 ABI {lib.gnb_abi_version()} != 1: rebuild')
+    if lib.gnb_abi_version() != ABI_VERSION:
+        raise RuntimeError(f'libgnnome_b200 ABI {lib.gnb_abi_version()} != {ABI_VERSION}: rebuild')
     _lib = lib
     return lib
 

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kThreads)
 node_update_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const float* __restrict__ e,
                    const float* __restrict__ F, const float* __restrict__ carry,
                    const float* __restrict__ h_in, const float* __restrict__ scale_h,
-                   const float* __restrict__ shift_h, float* __restrict__ h_out, int flags) {
+                   const float* __restrict__ shift_h, float* __restrict__ h_out, int flags, int chunk) {
   constexpr int TPN = H / 4;               // threads per node
   constexpr int NPB = kThreads / TPN;      // nodes in flight per CTA
   const int t = threadIdx.x % TPN, slot = threadIdx.x / TPN;
@@ -365,7 +365,7 @@ node_update_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, cons
     float4 f = zero;
     const int pa = g.in_ptr[i], pb = g.in_ptr[i + 1];
     if (pb > pa) {
-      const int c0 = pa / kChunk, c1 = (pb - 1) / kChunk;
+      const int c0 = pa / chunk, c1 = (pb - 1) / chunk;
       if (c0 == c1) {
         f = reinterpret_cast<const float4*>(F + i * H)[t];
       } else {
@@ -520,7 +520,7 @@ static int edge_forward_impl(const gnb_graph_t* g, const float* P, int64_t ldP, 
 template <int H>
 static int node_update_impl(const gnb_graph_t* g, const float* P, int64_t ldP, const float* e,
                             const float* F, const float* carry, const float* h_in,
-                            const float* scale_h, const float* shift_h, float* h_out, int flags,
+                            const float* scale_h, const float* shift_h, float* h_out, int flags, int chunk,
                             cudaStream_t stream) {
   int bps = 0;
   int rc = launch_cfg(node_update_kernel<H>, 0, &bps);
@@ -528,7 +528,7 @@ static int node_update_impl(const gnb_graph_t* g, const float* P, int64_t ldP, c
   constexpr int NPB = kThreads / (H / 4);
   int64_t items = (g->num_nodes + NPB - 1) / NPB;
   node_update_kernel<H><<<grid_for(items, bps * 4), kThreads, 0, stream>>>(
-      *g, P, ldP, e, F, carry, h_in, scale_h, shift_h, h_out, flags);
+      *g, P, ldP, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk);
   return check_launch("gnb_node_update");
 }
 
@@ -634,7 +634,8 @@ extern "C" int gnb_edge_forward(const gnb_graph_t* g, int H, const float* P, int
 extern "C" int gnb_node_update(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const float* e,
                                const float* F, const float* carry, const float* h_in,
                                const float* scale_h, const float* shift_h, float* h_out, int flags,
-                               void* stream) {
+                               int chunk, void* stream) {
+  GNB_REQUIRE(chunk > 0, "gnb_node_update: chunk must be the carry granularity of the edge pass that filled F/carry");
   int rc = check_graph(g);
   if (rc) return rc;
   if (g->num_nodes == 0) return 0;
@@ -646,7 +647,7 @@ extern "C" int gnb_node_update(const gnb_graph_t* g, int H, const float* P, int6
                   ((uintptr_t)carry % 16 == 0) && ((uintptr_t)h_in % 16 == 0) && ((uintptr_t)h_out % 16 == 0) &&
                   ((uintptr_t)scale_h % 16 == 0) && ((uintptr_t)shift_h % 16 == 0),
               "pointers must be 16-byte aligned");
-  GNB_DISPATCH_H(H, (node_update_impl<kH>(g, P, ldP, e, F, carry, h_in, scale_h, shift_h, h_out, flags,
+  GNB_DISPATCH_H(H, (node_update_impl<kH>(g, P, ldP, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk,
                                           (cudaStream_t)stream)));
 }
 

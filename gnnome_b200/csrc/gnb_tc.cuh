@@ -112,11 +112,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// 32-byte global load of 8 consecutive floats (one full sector per lane)
+// 32-byte global load of 8 consecutive floats (one full sector per lane).  Coherent path on purpose: the
+// edge kernel updates the same array in place (rows it has already consumed).
 __device__ __forceinline__ void ldg_f32x8(const float* p, float (&v)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
+               : "l"(p)
+               : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -55,6 +55,7 @@ class GraphIndex:
                        'gnb_graph_stage')
         self._keep = (src, dst)  # original-order endpoints (used by reversed())
         self._in_eid_long = None
+        self._tile_flags = {}
         del ws
 
     @property
@@ -68,11 +69,29 @@ class GraphIndex:
     def ref(self):
         return ctypes.byref(self.struct)
 
-    def num_chunks(self, H):
-        chunk = _lib.load().gnb_edge_chunk(H)
+    def chunk(self, H, backend='tc'):
+        """Carry granularity (edges per aggregation chunk) of the edge pass for this backend."""
+        lib = _lib.load()
+        chunk = lib.gnb_edge_chunk_tc(H) if backend == 'tc' else lib.gnb_edge_chunk(H)
         if chunk <= 0:
             raise RuntimeError(f'hidden_features={H} unsupported (32, 64, 128, 256)')
-        return max(1, -(-self.E // chunk))
+        return chunk
+
+    def num_chunks(self, H, backend='tc'):
+        return max(1, -(-self.E // self.chunk(H, backend)))
+
+    def tile_flags(self, H):
+        """Zeroed int32[tiles] + launch counter for the H=256 channel-half handshake of gnb_edge_forward_tc."""
+        tile = _lib.load().gnb_edge_tile_tc(H)
+        st = self._tile_flags.get(tile)
+        if st is None:
+            st = self._tile_flags[tile] = [torch.zeros(max(1, -(-self.E // tile)), dtype=torch.int32,
+                                                       device=self.device), 0]
+        if st[1] >= 2 ** 29:  # keep NH * epoch inside int32
+            st[0].zero_()
+            st[1] = 0
+        st[1] += 1
+        return st[0], st[1]
 
     def reversed(self):
         """Index of ``dgl.reverse(g)`` (train.py:165): same edge ids, endpoints swapped."""

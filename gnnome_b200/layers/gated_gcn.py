@@ -13,6 +13,22 @@ from .. import _lib, ops
 from ..graph import GraphIndex
 
 
+_BACKEND = 'tc'
+
+
+def set_backend(name):
+    """'tc' (default): dense products on the tcgen05 tensor cores (fp16 hi/lo split, fp32 accumulate);
+    'ffma': the CUDA-core fp32 kernels (bring-up path, kept as an on-device cross-check)."""
+    global _BACKEND
+    if name not in ('tc', 'ffma'):
+        raise ValueError(name)
+    _BACKEND = name
+
+
+def get_backend():
+    return _BACKEND
+
+
 def _bn_affine(norm, device):
     """Eval-mode BatchNorm1d as a per-channel affine, computed in fp64 (gated_gcn_full.py:37-38)."""
     var = norm.running_var.detach().double()
@@ -52,9 +68,18 @@ class _GatedGCNBase(nn.Module):
         return (_lib.GNB_F_SYMMETRIC if self._symmetric else 0) | (_lib.GNB_F_RESIDUAL if self.residual else 0)
 
     def _pack(self, device):
-        """Kernel-side views of the parameters: the concatenated k-major node projection with the
-        (B1, A2) rows interleaved per channel, the k-major edge projection, and the eval-mode norm
-        affines (b_B3 folded into the edge shift).  Recomputed per call (a few KB..MB)."""
+        """Kernel-side views of the parameters (see _pack_now), cached until a parameter / buffer
+        changes (torch bumps ``_version`` on every in-place update) or moves."""
+        key = tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers()))
+        key += (str(device), _BACKEND)
+        cache = self.__dict__.get('_pack_cache')
+        if cache is None or cache[0] != key:
+            cache = self.__dict__['_pack_cache'] = (key, self._pack_now(device))
+        return cache[1]
+
+    def _pack_now(self, device):
+        """The concatenated node projection with the (B1, A2) rows interleaved per channel, the
+        edge projection, and the eval-mode norm affines (b_B3 folded into the edge shift)."""
         H = self.out_channels
         dev = dict(device=device, dtype=torch.float32)
         w = lambda lin: lin.weight.detach().to(**dev)
@@ -66,9 +91,13 @@ class _GatedGCNBase(nn.Module):
             blocks_b.append(b(self.A_3))
         blocks_w.append(w(self.A_1))
         blocks_b.append(b(self.A_1))
-        Wn_t = torch.cat(blocks_w, dim=0).t().contiguous()           # [H_in][5H or 4H]
+        Wn = torch.cat(blocks_w, dim=0).contiguous()                 # [5H or 4H][H_in] (nn.Linear layout)
         bn = torch.cat(blocks_b, dim=0).contiguous()
-        We_t = w(self.B_3).t().contiguous()                          # [H_in][H]
+        if _BACKEND == 'tc':
+            Wn_t, We_t = ops.pack_linear_tc(Wn), ops.pack_linear_tc(w(self.B_3).contiguous())
+        else:
+            Wn_t = Wn.t().contiguous()                               # k-major [H_in][5H or 4H]
+            We_t = w(self.B_3).t().contiguous()                      # k-major [H_in][H]
         if self.normalization == 'batch':
             se, te = _bn_affine(self.bn_e, device)
             sh, th = _bn_affine(self.bn_h, device)
@@ -99,15 +128,23 @@ class _GatedGCNBase(nn.Module):
         if Fb is None or Fb.shape != (gi.N, H):
             Fb = ws['F'] = torch.empty((gi.N, H), dtype=torch.float32, device=dev)
         carry = ws.get('carry')
-        if carry is None or carry.shape != (gi.num_chunks(H), 4, H):
-            carry = ws['carry'] = torch.empty((gi.num_chunks(H), 4, H), dtype=torch.float32, device=dev)
+        n_chunks = gi.num_chunks(H, _BACKEND)
+        if carry is None or carry.shape != (n_chunks, 4, H):
+            carry = ws['carry'] = torch.empty((n_chunks, 4, H), dtype=torch.float32, device=dev)
         h_out = ws.pop('h_spare', None)
         if h_out is None or h_out.shape != h.shape or h_out.data_ptr() == h.data_ptr():
             h_out = torch.empty_like(h)
         flags = self._flags()
-        ops.node_linear(h, pk['Wn_t'], pk['bn'], out=P)
-        ops.edge_forward(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry, flags)
-        ops.node_update(gi, H, P, e_pos, Fb, carry, h, pk['scale_h'], pk['shift_h'], h_out, flags)
+        if _BACKEND == 'tc':
+            ops.node_linear_tc(h, pk['Wn_t'], pk['bn'], n_blocks * H, out=P)
+            tile_flags, epoch = gi.tile_flags(H) if H > 128 else (None, 0)
+            ops.edge_forward_tc(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry,
+                                tile_flags, epoch, flags)
+        else:
+            ops.node_linear(h, pk['Wn_t'], pk['bn'], out=P)
+            ops.edge_forward(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry, flags)
+        ops.node_update(gi, H, P, e_pos, Fb, carry, h, pk['scale_h'], pk['shift_h'], h_out, flags,
+                        gi.chunk(H, _BACKEND))
         ws['h_spare'] = h  # ping-pong: the caller no longer needs the input h
         return h_out, e_pos
 

@@ -124,12 +124,21 @@ def edge_forward(gi: GraphIndex, H, P, We_t, scale_e, shift_e, e, F, carry, flag
                                         current_stream_ptr(e.device)), 'gnb_edge_forward')
 
 
-def node_update(gi: GraphIndex, H, P, e, F, carry, h_in, scale_h, shift_h, h_out, flags):
+def edge_forward_tc(gi: GraphIndex, H, P, Wp, scale_e, shift_e, e, F, carry, tile_flags, epoch, flags):
+    lib = _lib.load()
+    with _logged('gnb_edge_forward_tc', e.device):
+        _lib.check(lib.gnb_edge_forward_tc(gi.ref(), H, _f32(P, 'P'), P.stride(0), Wp.data_ptr(),
+                                           _f32(scale_e, 'scale_e'), _f32(shift_e, 'shift_e'), _f32(e, 'e'),
+                                           _f32(F, 'F'), _f32(carry, 'carry'), _opt(tile_flags), epoch, flags,
+                                           current_stream_ptr(e.device)), 'gnb_edge_forward_tc')
+
+
+def node_update(gi: GraphIndex, H, P, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk):
     lib = _lib.load()
     with _logged('gnb_node_update', h_in.device):
         _lib.check(lib.gnb_node_update(gi.ref(), H, _f32(P, 'P'), P.stride(0), _f32(e, 'e'), _f32(F, 'F'),
                                        _f32(carry, 'carry'), _f32(h_in, 'h_in'), _f32(scale_h, 'scale_h'),
-                                       _f32(shift_h, 'shift_h'), _f32(h_out, 'h_out'), flags,
+                                       _f32(shift_h, 'shift_h'), _f32(h_out, 'h_out'), flags, chunk,
                                        current_stream_ptr(h_in.device)), 'gnb_node_update')
 
 

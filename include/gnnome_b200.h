@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 1
+#define GNB_ABI_VERSION 2
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -91,6 +91,20 @@ int gnb_pack_linear_tc(const float* W, int M, int K, void* Wp, void* stream);
 int gnb_node_linear_tc(const float* X, int64_t rows, int K, const void* Wp, const float* bias, int M,
                        float* out, int64_t ld_out, void* stream);
 
+/* Carry granularity (edges per aggregation chunk) and tile size of gnb_edge_forward_tc. */
+int gnb_edge_chunk_tc(int H);
+int gnb_edge_tile_tc(int H);
+
+/* Tensor-core edition of gnb_edge_forward: same contract, with the edge weight given as
+ * gnb_pack_linear_tc(B_3.weight [H][H]) and carry sized ceil(E / gnb_edge_chunk_tc(H)) x 4 x H.
+ * For H = 256 the two 128-channel halves of a tile run on different CTAs and both read whole rows of e
+ * before either overwrites its half: tile_flags is a caller-owned int32[ceil(E / gnb_edge_tile_tc(H))],
+ * zeroed once, and epoch = 1, 2, 3, ... counts the launches that used it since (unused for H < 256).
+ * e must be 32-byte aligned. */
+int gnb_edge_forward_tc(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
+                        const float* scale_e, const float* shift_e, float* e, float* F, float* carry,
+                        int32_t* tile_flags, int epoch, int flags, void* stream);
+
 /* Number of consecutive edge positions one aggregation chunk covers (carry granularity). */
 int gnb_edge_chunk(int H);
 
@@ -113,11 +127,12 @@ int gnb_edge_forward(const gnb_graph_t* g, int H, const float* P, int64_t ldP,
 /* Reverse aggregation over the src-CSR fused with the node update (gated_gcn_full.py:124-137):
  *   Bk_i = sum_{q: src_q = i} sigmoid(e'_q) * P[dst_q][A3h] / (sum_q sigmoid(e'_q) + 1e-6)   (symmetric only)
  *   h'_i = relu((P[i][A1h] + F_i + Bk_i) * scale_h + shift_h) (+ h_i if GNB_F_RESIDUAL)
+ * chunk = carry granularity of the edge pass that produced F / carry (gnb_edge_chunk or gnb_edge_chunk_tc).
  * Dropout (gated_gcn_full.py:139) is left to the caller (torch RNG semantics). */
 int gnb_node_update(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const float* e,
                     const float* F, const float* carry, const float* h_in,
                     const float* scale_h, const float* shift_h, float* h_out, int flags,
-                    void* stream);
+                    int chunk, void* stream);
 
 /* ScorePredictor (score_predictor.py:12-24) with W1 = [W1s | W1d | W1e] split so that the node
  * halves are projected once per node:  S[n] = [x_n * W1s^T | x_n * W1d^T + b1]  ([N][2*hs], from

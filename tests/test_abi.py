@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), f'{name} missing from {_lib.LIB_PATH}'
     assert set(_declared()) == set(_lib.SIGNATURES), 'ctypes signature table out of sync with the header'
-    assert _lib.load().gnb_abi_version() == 1
+    assert _lib.load().gnb_abi_version() == _lib.ABI_VERSION
 
 
 def test_argument_errors_do_not_need_a_gpu():

@@ -21,6 +21,14 @@ def gnb():
     return gnnome_b200
 
 
+@pytest.fixture(params=['tc', 'ffma'])
+def backend(request, gnb):
+    """'tc' = tcgen05 tensor-core kernels (the product path), 'ffma' = CUDA-core fp32 kernels."""
+    gnb.set_backend(request.param)
+    yield request.param
+    gnb.set_backend('tc')
+
+
 def _graph(n, m, seed):
     src, dst = synth.make_assembly_graph(n, m, seed=seed)
     x, e = synth.make_features(src, dst, n, seed=seed)
@@ -70,6 +78,22 @@ def test_node_linear(gnb, rows, K, M):
     out = ops.node_linear(a.cuda(), w.t().contiguous().cuda(), b.cuda())
     ref = (a.double() @ w.double().t() + b.double())
     assert (out.cpu().double() - ref).abs().max().item() < 2e-5
+    # tensor-core edition: fp16 (hi, lo) split, three MMAs, fp32 accumulate -- same tolerance
+    out_tc = ops.node_linear_tc(a.cuda(), ops.pack_linear_tc(w.cuda()), b.cuda(), M)
+    assert (out_tc.cpu().double() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize('scale', [1e-3, 1.0, 300.0, 3e4])
+def test_node_linear_tc_dynamic_range(gnb, scale):
+    """The fp16 split keeps fp32-level accuracy up to |x| ~ 1e5; below |x| ~ 1 the fp16 subnormal
+    range puts an ABSOLUTE floor of ~2^-21 per input element on the error."""
+    from gnnome_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(300, 256, generator=g) * scale
+    w, b = torch.randn(640, 256, generator=g) / 16, torch.zeros(640)
+    out = ops.node_linear_tc(a.cuda(), ops.pack_linear_tc(w.cuda()), b.cuda(), 640)
+    ref = a.double() @ w.double().t()
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-5 * max(scale, 1.0)
 
 
 @pytest.mark.parametrize('rows,H', [(5, 64), (1000, 256), (64, 32)])
@@ -103,7 +127,7 @@ def _hub_graph(n, m, hub_deg, seed):
 
 @pytest.mark.parametrize('H', [32, 64, 128, 256])
 @pytest.mark.parametrize('sym', [True, False])
-def test_single_layer_vs_oracle(gnb, H, sym):
+def test_single_layer_vs_oracle(gnb, backend, H, sym):
     n = 700
     src, dst = _hub_graph(n, 3000, 1500, seed=H)
     m = src.numel()
@@ -131,7 +155,7 @@ def test_single_layer_vs_oracle(gnb, H, sym):
 
 # ---------------------------------------------------------------- whole model vs reference goldens
 @pytest.mark.parametrize('name', ['sym_shipped_tiny', 'sym_shipped_2k'])
-def test_shipped_model_vs_reference_golden(gnb, golden, shipped_weights, name):
+def test_shipped_model_vs_reference_golden(gnb, backend, golden, shipped_weights, name):
     g = golden(name)
     model = gnb.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch', dropout=None)
     model.load_state_dict(shipped_weights, strict=True)
@@ -163,7 +187,7 @@ def test_other_models_vs_reference_golden(gnb, golden, name, ctor):
 
 
 @pytest.mark.parametrize('H,L,n,m', [(64, 8, 20000, 120000), (128, 4, 10000, 60000), (256, 3, 6000, 36000)])
-def test_model_vs_oracle_fp64(gnb, shipped_weights, H, L, n, m):
+def test_model_vs_oracle_fp64(gnb, backend, shipped_weights, H, L, n, m):
     """Against the fp64 evaluation of the oracle ("true value"): our error must stay within the
     tolerance and within a small multiple of the fp32 reference's own error."""
     src, dst, n, x, e = _graph(n, m, seed=H)
@@ -208,7 +232,7 @@ def test_edge_relabelling_equivariance(gnb, shipped_weights):
     assert _prob_err(a[perm], b) <= PROB_TOL
 
 
-def test_empty_and_degenerate_graphs(gnb, shipped_weights):
+def test_empty_and_degenerate_graphs(gnb, backend, shipped_weights):
     model = gnb.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch')
     model.load_state_dict(shipped_weights)
     model.eval()
