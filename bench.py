@@ -39,6 +39,7 @@ WORKLOADS = {
     'cfg3': (10_000_000, 60_000_000, 256, 8, 'synthetic power-law assembly graph 10M nodes / 60M edges, hidden=256, L=8'),
     'cfg2': (1_000_000, 6_000_000, 128, 8, 'synthetic power-law assembly graph 1M nodes / 6M edges, hidden=128, L=8'),
     'cfg2s': (1_000_000, 6_000_000, 64, 8, 'synthetic 1M nodes / 6M edges, hidden=64 (shipped-model width), L=8'),
+    'mid': (2_000_000, 12_000_000, 256, 8, 'synthetic 2M nodes / 12M edges, hidden=256, L=8 (profiling size)'),
     'small': (100_000, 600_000, 256, 8, 'synthetic 100k nodes / 600k edges, hidden=256, L=8 (debug size)'),
 }
 CPU_SAMPLE = (40_000, 240_000)      # bounded sample of the workload for the CPU arm (same H, L, generator)

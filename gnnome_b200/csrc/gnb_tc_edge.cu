@@ -7,13 +7,15 @@
 // halves of a tile run on neighbouring CTAs) with its W_B3 block resident in TMEM, and walks 64-edge tiles
 // of the dst-sorted edge array:
 //   warp 0      : MMA issue (D^T[channel][edge] = W * e^T, fp16 hi/lo split, fp32 accumulate in TMEM)
-//   warps 1..4  : producers: e rows (fp32, coalesced 32-byte lane loads) -> fp16 (hi, lo) operand images
-//   warps 5..20 : epilogue: 2 accumulator buffers x 4 TMEM lane quarters x 2 chunks of 32 edges.
+//   warps 1..8  : producers: e rows (fp32, coalesced 32-byte lane loads) -> fp16 (hi, lo) operand images
+//   warps 9..24 : epilogue: 2 accumulator buffers x 4 TMEM lane quarters x 2 chunks of 32 edges.
 //                 A thread owns ONE channel and walks its 32 consecutive edges: gathers of the
 //                 (B1h, A2h) node rows are 128/256-byte coalesced across the warp, the per-destination
 //                 sums are register accumulators closed at warp-uniform segment boundaries (no atomics,
 //                 fixed summation order).  Segments that straddle a 32-edge chunk leave partial sums in
 //                 carry[chunk][4][H], resolved by gnb_node_update.
+#include <type_traits>
+
 #include "gnb_tc.cuh"
 
 namespace gnb {
@@ -21,9 +23,11 @@ namespace tc {
 
 constexpr int kEdgeNT = 64;      // edges per tile (MMA N)
 constexpr int kEdgeChunk = 32;   // edges per epilogue warp = carry granularity
-constexpr int kEdgeProducerWarps = 4;
+constexpr int kEdgeProducerWarps = 8;
 constexpr int kEdgeEpiWarps = 16;
-constexpr int kEdgeThreads = 32 * (1 + kEdgeProducerWarps + kEdgeEpiWarps);
+constexpr int kEdgeFirstEpiWarp = 1 + kEdgeProducerWarps;   // must be 1 (mod 4): 4 consecutive warps cover the 4 TMEM lane quarters
+constexpr int kEdgeThreads = 32 * (kEdgeFirstEpiWarp + kEdgeEpiWarps);
+static_assert(kEdgeFirstEpiWarp % 4 == 1, "epilogue warp numbering");
 
 template <int H>
 struct EdgeTcCfg {
@@ -83,7 +87,7 @@ edge_forward_tc_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 5 && warp < 9) load_weights_to_tmem<H>(Wp + (size_t)half * 2 * kM * H, tmem_base, warp & 3, lane);
+  if (warp >= kEdgeFirstEpiWarp && warp < kEdgeFirstEpiWarp + 4) load_weights_to_tmem<H>(Wp + (size_t)half * 2 * kM * H, tmem_base, warp & 3, lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -120,7 +124,7 @@ edge_forward_tc_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, 
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int ew = warp - 5;
+    const int ew = warp - kEdgeFirstEpiWarp;
     const int grp = ew >> 3, sub = (ew >> 2) & 1, q = warp & 3;
     const int cl = q * 32 + lane;            // TMEM lane = channel within the CTA's block
     const bool ch_ok = cl < C::HC;           // warp-uniform (HC is a multiple of 32)
@@ -129,34 +133,37 @@ edge_forward_tc_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, 
     const bool residual = flags & GNB_F_RESIDUAL;
     const float* Pc = P + 2 * c;             // (B1h[c], A2h[c]) interleaved
     const float* Pb2 = P + 2 * H + c;        // B2h[c]
+    constexpr unsigned kFull = 0xffffffffu;
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       if ((i & 1) != grp) continue;
       const int64_t cs = t * kEdgeNT + sub * kEdgeChunk;
       const bool live = cs < E && ch_ok;     // warp-uniform
       const int n = live ? (int)((E - cs < kEdgeChunk) ? (E - cs) : kEdgeChunk) : 0;
-      int my_src = -1, my_dst = -1, head_dst = -1, tail_dst = -1;
+      int my_src = 0, my_dst = -1, head_dst = -1, tail_dst = -1;
+      unsigned segmask = 0;                  // bit j: edge j of the chunk opens a new destination segment
       if (live) {
-        if (lane < n) {
-          my_src = g.in_src[cs + lane];
-          my_dst = g.in_dst[cs + lane];
-        }
+        const int64_t pl = cs + (lane < n ? lane : n - 1);   // tail lanes repeat the last edge (loads only)
+        my_src = g.in_src[pl];
+        my_dst = g.in_dst[pl];
         const int prev_dst = (cs > 0) ? g.in_dst[cs - 1] : -1;
         const int next_dst = (cs + n < E) ? g.in_dst[cs + n] : -1;
-        const int first_dst = __shfl_sync(0xffffffffu, my_dst, 0);
-        const int last_dst = __shfl_sync(0xffffffffu, my_dst, n - 1);
+        const int up = __shfl_up_sync(kFull, my_dst, 1);
+        segmask = __ballot_sync(kFull, lane == 0 || (lane < n && my_dst != up));
+        const int first_dst = __shfl_sync(kFull, my_dst, 0);
+        const int last_dst = __shfl_sync(kFull, my_dst, n - 1);
         if (prev_dst == first_dst) head_dst = first_dst;
         if (next_dst == last_dst) tail_dst = last_dst;
       }
       mbar_wait(&dfull[grp], (i >> 1) & 1);
       tc_fence_after();
-      uint32_t zr[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + grp * kEdgeNT + sub * kEdgeChunk, zr);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dempty[grp]);
-      if (!live) continue;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + grp * kEdgeNT + sub * kEdgeChunk;
+      if (!live) {  // nothing to compute, but the accumulator buffer still has to be handed back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dempty[grp]);
+        continue;
+      }
       if (C::NH > 1) {  // the other half must have read tile t before we overwrite our channels of it
         if (lane == 0) {
           while (ld_acquire(tile_flags + t) < C::NH * epoch) __nanosleep(32);
@@ -164,63 +171,93 @@ edge_forward_tc_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, 
         __syncwarp();
       }
       const int64_t chunk = cs / kEdgeChunk;
+      float* erow = e + cs * H + c;          // this thread's channel of the chunk's first edge
       int cur = -1;
-      float num = 0.f, den = 0.f, b2 = 0.f;
+      float num = 0.f, den = 0.f, b2s = 0.f;
+
+      // Software pipeline over eight batches of four edges: the gathers of batch b+1 are in flight while
+      // batch b is computed.  fa = (B1h, A2h)[src], fe = layer input (residual), fb = B2h[dst] (fetched only
+      // where a destination segment opens).  kTail = the one ragged chunk at the end of the edge array.
+      constexpr int kEB = 4;   // edges per batch
+      float2 ba[2][kEB];
+      float ein[2][kEB], b2v[2][kEB];
+      auto fetch = [&](auto tail, int b, float2 (&fa)[kEB], float (&fe)[kEB], float (&fb)[kEB]) {
+        constexpr bool kTail = decltype(tail)::value;
+        const unsigned mb = segmask >> (b * kEB);
+        const float* eb = erow + (int64_t)b * kEB * H;
 #pragma unroll
-      for (int j0 = 0; j0 < kEdgeChunk; j0 += 8) {
-        if (j0 < n) {
-          float2 ba[8];
-          float ein[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int sj = __shfl_sync(0xffffffffu, my_src, j0 + u);
-            ba[u] = make_float2(0.f, 0.f);
-            ein[u] = 0.f;
-            if (j0 + u < n) {
-              ba[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj * ldP));
-              ein[u] = e[(cs + j0 + u) * H + c];
-            }
+        for (int u = 0; u < kEB; ++u) {
+          const int sj = __shfl_sync(kFull, my_src, b * kEB + u);
+          fa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj * ldP));
+          if (kTail) fe[u] = (b * kEB + u < n) ? eb[u * H] : 0.f;
+          else fe[u] = eb[u * H];
+          fb[u] = 0.f;
+          if (mb & (1u << u)) {   // warp-uniform
+            const int dj = __shfl_sync(kFull, my_dst, b * kEB + u);
+            fb[u] = __ldg(Pb2 + (int64_t)dj * ldP);
           }
+        }
+      };
+      auto compute = [&](auto tail, int b, const float2 (&fa)[kEB], const float (&fe)[kEB], const float (&fb)[kEB]) {
+        constexpr bool kTail = decltype(tail)::value;
+        uint32_t zr[kEB];
+        tmem_ld4(taddr + b * kEB, zr);
+        tmem_ld_wait();
+        if (b == kEdgeChunk / kEB - 1) {   // last read of this accumulator buffer: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dempty[grp]);
+        }
+        const unsigned mb = segmask >> (b * kEB);
+        float* eb = erow + (int64_t)b * kEB * H;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = j0 + u;
-            const int d = __shfl_sync(0xffffffffu, my_dst, j);
-            if (j < n) {
-              if (d != cur) {
-                if (cur >= 0) {
-                  if (cur == head_dst) {
-                    carry[(chunk * 4 + 0) * H + c] = num;
-                    carry[(chunk * 4 + 1) * H + c] = den;
-                  } else {
-                    F[(int64_t)cur * H + c] = num / (den + kGateEps);
-                  }
-                }
-                cur = d;
-                num = 0.f;
-                den = 0.f;
-                b2 = __ldg(Pb2 + (int64_t)d * ldP);
+        for (int u = 0; u < kEB; ++u) {
+          if (mb & (1u << u)) {          // warp-uniform: close the running segment, open the next
+            if (cur >= 0) {
+              if (cur == head_dst) {
+                carry[(chunk * 4 + 0) * H + c] = num;
+                carry[(chunk * 4 + 1) * H + c] = den;
+              } else {
+                F[(int64_t)cur * H + c] = gate_div(num, den);
               }
-              float v = fmaf(__uint_as_float(zr[j]) + ba[u].x + b2, sc, sh);
-              v = fmaxf(v, 0.f);
-              if (residual) v += ein[u];
-              e[(cs + j) * H + c] = v;
-              const float sg = sigmoidf_fast(v);
-              num = fmaf(sg, ba[u].y, num);
-              den += sg;
             }
+            cur = __shfl_sync(kFull, my_dst, b * kEB + u);
+            num = 0.f;
+            den = 0.f;
+            b2s = fmaf(fb[u], sc, sh);
+          }
+          float v = fmaf(__uint_as_float(zr[u]) + fa[u].x, sc, b2s);
+          v = fmaxf(v, 0.f);
+          if (residual) v += fe[u];
+          if (!kTail || b * kEB + u < n) {
+            eb[u * H] = v;
+            const float sg = sigmoidf_fast(v);
+            num = fmaf(sg, fa[u].y, num);
+            den += sg;
           }
         }
-      }
-      if (cur >= 0) {
-        if (cur == tail_dst) {
-          carry[(chunk * 4 + 2) * H + c] = num;
-          carry[(chunk * 4 + 3) * H + c] = den;
-        } else if (cur == head_dst) {
-          carry[(chunk * 4 + 0) * H + c] = num;
-          carry[(chunk * 4 + 1) * H + c] = den;
-        } else {
-          F[(int64_t)cur * H + c] = num / (den + kGateEps);
+      };
+      auto run_chunk = [&](auto tail) {
+        fetch(tail, 0, ba[0], ein[0], b2v[0]);
+#pragma unroll 1
+        for (int b = 0; b < kEdgeChunk / kEB; b += 2) {
+          fetch(tail, b + 1, ba[1], ein[1], b2v[1]);
+          compute(tail, b, ba[0], ein[0], b2v[0]);
+          if (b + 2 < kEdgeChunk / kEB) fetch(tail, b + 2, ba[0], ein[0], b2v[0]);
+          compute(tail, b + 1, ba[1], ein[1], b2v[1]);
         }
+      };
+      if (n == kEdgeChunk) run_chunk(std::false_type{});
+      else run_chunk(std::true_type{});
+      // close the segment that is still open at the end of the chunk
+      if (cur == tail_dst) {
+        carry[(chunk * 4 + 2) * H + c] = num;
+        carry[(chunk * 4 + 3) * H + c] = den;
+      } else if (cur == head_dst) {
+        carry[(chunk * 4 + 0) * H + c] = num;
+        carry[(chunk * 4 + 1) * H + c] = den;
+      } else {
+        F[(int64_t)cur * H + c] = gate_div(num, den);
       }
     }
   }

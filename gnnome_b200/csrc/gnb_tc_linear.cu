@@ -8,8 +8,8 @@
 // stays in TMEM) and walks row tiles worker, worker + workers, ...  All channel blocks visit the same row
 // tile at about the same time, so X is read from HBM once and from L2 nblk times.
 //   warp 0        : TMEM allocation, MMA issue (one lane)
-//   warps 1..4    : producers  (global fp32 rows -> fp16 hi/lo operand images in shared memory)
-//   warps 5..12   : epilogue, two groups of four warps (one warp per TMEM lane quarter), group g drains
+//   warps 1..8    : producers  (global fp32 rows -> fp16 hi/lo operand images in shared memory)
+//   warps 9..16   : epilogue, two groups of four warps (one warp per TMEM lane quarter), group g drains
 //                   accumulator buffer g: +bias, coalesced 128-byte stores
 #include "gnb_tc.cuh"
 
@@ -17,8 +17,10 @@ namespace gnb {
 namespace tc {
 
 constexpr int kLinNT = 64;
-constexpr int kLinProducerWarps = 4;
-constexpr int kLinThreads = 32 * (1 + kLinProducerWarps + 8);
+constexpr int kLinProducerWarps = 8;
+constexpr int kLinFirstEpiWarp = 1 + kLinProducerWarps;  // 1 (mod 4): 4 consecutive warps cover the 4 TMEM lane quarters
+constexpr int kLinThreads = 32 * (kLinFirstEpiWarp + 8);
+static_assert(kLinFirstEpiWarp % 4 == 1, "epilogue warp numbering");
 
 template <int K>
 struct LinCfg {
@@ -67,7 +69,7 @@ node_linear_tc_kernel(const float* __restrict__ X, int64_t rows, const __half* _
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 5 && warp < 9) {  // first epilogue group doubles as the weight loader
+  if (warp >= kLinFirstEpiWarp && warp < kLinFirstEpiWarp + 4) {  // first epilogue group doubles as the weight loader
     load_weights_to_tmem<K>(Wp + (size_t)cb * 2 * kM * K, tmem_base, warp & 3, lane);
   }
   tc_fence_before();
@@ -103,7 +105,7 @@ node_linear_tc_kernel(const float* __restrict__ X, int64_t rows, const __half* _
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int g = (warp - 5) >> 2, q = warp & 3;
+    const int g = (warp - kLinFirstEpiWarp) >> 2, q = warp & 3;
     const int ch = cb * kM + q * 32 + lane;
     const bool ch_ok = ch < M;
     const float b = ch_ok ? bias[ch] : 0.f;
