@@ -62,17 +62,18 @@ __global__ void row_ptr_kernel(const int32_t* __restrict__ keys, int64_t n, int6
   for (int64_t v = prev + 1; v <= cur; ++v) ptr[v] = (int32_t)p;
 }
 
+// ld_in / ld_out: row strides in float4 units
 template <bool kScatter>
-__global__ void move_rows_kernel(const float4* __restrict__ in, const int32_t* __restrict__ idx,
-                                 int64_t rows, int w4, float4* __restrict__ out) {
+__global__ void move_rows_kernel(const float4* __restrict__ in, int64_t ld_in, const int32_t* __restrict__ idx,
+                                 int64_t rows, int w4, float4* __restrict__ out, int64_t ld_out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = rows * w4;
   for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / w4;
     int c = (int)(i - r * w4);
     int64_t other = idx[r];
-    if (kScatter) out[other * w4 + c] = in[i];
-    else out[i] = in[other * w4 + c];
+    if (kScatter) out[other * ld_out + c] = in[r * ld_in + c];
+    else out[r * ld_out + c] = in[other * ld_in + c];
   }
 }
 
@@ -151,9 +152,10 @@ extern "C" int gnb_graph_stage(const int32_t* src, const int32_t* dst, gnb_graph
   return check_launch("gnb_graph_stage");
 }
 
-static int move_rows(bool scatter, const float* in, const int32_t* idx, int64_t rows, int W,
-                     float* out, void* stream_) {
+static int move_rows(bool scatter, const float* in, int64_t ld_in, const int32_t* idx, int64_t rows, int W,
+                     float* out, int64_t ld_out, void* stream_) {
   GNB_REQUIRE(W > 0 && W % 4 == 0, "row width %d must be a positive multiple of 4", W);
+  GNB_REQUIRE(ld_in >= W && ld_out >= W && ld_in % 4 == 0 && ld_out % 4 == 0, "row strides must be multiples of 4, >= W");
   GNB_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0), "rows must be 16-byte aligned");
   if (rows == 0) return 0;
   GNB_REQUIRE(in && idx && out, "null pointer");
@@ -162,18 +164,23 @@ static int move_rows(bool scatter, const float* in, const int32_t* idx, int64_t 
                                                                               : (int64_t)sm_count() * 16);
   cudaStream_t stream = (cudaStream_t)stream_;
   if (scatter)
-    move_rows_kernel<true><<<blocks, 256, 0, stream>>>((const float4*)in, idx, rows, W / 4, (float4*)out);
+    move_rows_kernel<true><<<blocks, 256, 0, stream>>>((const float4*)in, ld_in / 4, idx, rows, W / 4, (float4*)out, ld_out / 4);
   else
-    move_rows_kernel<false><<<blocks, 256, 0, stream>>>((const float4*)in, idx, rows, W / 4, (float4*)out);
+    move_rows_kernel<false><<<blocks, 256, 0, stream>>>((const float4*)in, ld_in / 4, idx, rows, W / 4, (float4*)out, ld_out / 4);
   return check_launch("gnb_move_rows");
 }
 
 extern "C" int gnb_gather_rows(const float* in, const int32_t* idx, int64_t rows, int W, float* out,
                                void* stream) {
-  return move_rows(false, in, idx, rows, W, out, stream);
+  return move_rows(false, in, W, idx, rows, W, out, W, stream);
+}
+
+extern "C" int gnb_gather_rows_ld(const float* in, int64_t ld_in, const int32_t* idx, int64_t rows, int W,
+                                  float* out, int64_t ld_out, void* stream) {
+  return move_rows(false, in, ld_in, idx, rows, W, out, ld_out, stream);
 }
 
 extern "C" int gnb_scatter_rows(const float* in, const int32_t* idx, int64_t rows, int W, float* out,
                                 void* stream) {
-  return move_rows(true, in, idx, rows, W, out, stream);
+  return move_rows(true, in, W, idx, rows, W, out, W, stream);
 }

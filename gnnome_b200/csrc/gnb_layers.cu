@@ -323,20 +323,22 @@ __global__ void __launch_bounds__(kThreads)
 node_update_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const float* __restrict__ e,
                    const float* __restrict__ F, const float* __restrict__ carry,
                    const float* __restrict__ h_in, const float* __restrict__ scale_h,
-                   const float* __restrict__ shift_h, float* __restrict__ h_out, int flags, int chunk) {
+                   const float* __restrict__ shift_h, float* __restrict__ h_out, int flags, int chunk,
+                   int64_t node_begin, int64_t node_end, const int32_t* __restrict__ xp_ptr,
+                   const int32_t* __restrict__ xp_row, const float* __restrict__ xp_buf,
+                   float* __restrict__ partial_out) {
   constexpr int TPN = H / 4;               // threads per node
   constexpr int NPB = kThreads / TPN;      // nodes in flight per CTA
   const int t = threadIdx.x % TPN, slot = threadIdx.x / TPN;
   const bool sym = flags & GNB_F_SYMMETRIC, residual = flags & GNB_F_RESIDUAL;
   const int a1_off = sym ? 4 * H : 3 * H;
-  const float4 sc = reinterpret_cast<const float4*>(scale_h)[t];
-  const float4 sh = reinterpret_cast<const float4*>(shift_h)[t];
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int64_t N = g.num_nodes;
-  for (int64_t i = (int64_t)blockIdx.x * NPB + slot; i < N; i += (int64_t)gridDim.x * NPB) {
+  const float4 sc = partial_out ? zero : reinterpret_cast<const float4*>(scale_h)[t];
+  const float4 sh = partial_out ? zero : reinterpret_cast<const float4*>(shift_h)[t];
+  for (int64_t i = node_begin + (int64_t)blockIdx.x * NPB + slot; i < node_end; i += (int64_t)gridDim.x * NPB) {
     // ---- Bk: gate-normalised sum over out-edges ------------------------------------------------
     float4 bk = zero;
-    if (sym) {
+    if (sym || partial_out) {
       float4 num = zero, den = zero;
       const int qa = g.out_ptr[i], qb = g.out_ptr[i + 1];
       for (int q0 = qa; q0 < qb; q0 += 4) {
@@ -357,6 +359,18 @@ node_update_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, cons
             num = f4_fma(sg, av[u], num);
             den = f4_add(den, sg);
           }
+        }
+      }
+      if (partial_out) {  // multi-GPU: un-normalised partial sums of a halo source node, for its owner
+        reinterpret_cast<float4*>(partial_out + (i - node_begin) * 2 * H)[t] = num;
+        reinterpret_cast<float4*>(partial_out + (i - node_begin) * 2 * H + H)[t] = den;
+        continue;
+      }
+      if (xp_ptr) {       // multi-GPU: partial sums other ranks computed for this node, in rank order
+        for (int r = xp_ptr[i], re = xp_ptr[i + 1]; r < re; ++r) {
+          const float* row = xp_buf + (int64_t)xp_row[r] * 2 * H;
+          num = f4_add(num, reinterpret_cast<const float4*>(row)[t]);
+          den = f4_add(den, reinterpret_cast<const float4*>(row + H)[t]);
         }
       }
       bk = f4_gate_div(num, den);
@@ -521,15 +535,17 @@ template <int H>
 static int node_update_impl(const gnb_graph_t* g, const float* P, int64_t ldP, const float* e,
                             const float* F, const float* carry, const float* h_in,
                             const float* scale_h, const float* shift_h, float* h_out, int flags, int chunk,
-                            cudaStream_t stream) {
+                            int64_t node_begin, int64_t node_end, const int32_t* xp_ptr, const int32_t* xp_row,
+                            const float* xp_buf, float* partial_out, cudaStream_t stream) {
   int bps = 0;
   int rc = launch_cfg(node_update_kernel<H>, 0, &bps);
   if (rc) return rc;
   constexpr int NPB = kThreads / (H / 4);
-  int64_t items = (g->num_nodes + NPB - 1) / NPB;
+  int64_t items = (node_end - node_begin + NPB - 1) / NPB;
   node_update_kernel<H><<<grid_for(items, bps * 4), kThreads, 0, stream>>>(
-      *g, P, ldP, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk);
-  return check_launch("gnb_node_update");
+      *g, P, ldP, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk, node_begin, node_end, xp_ptr, xp_row,
+      xp_buf, partial_out);
+  return check_launch(partial_out ? "gnb_reverse_partial" : "gnb_node_update");
 }
 
 template <int H, int HS>
@@ -634,12 +650,17 @@ extern "C" int gnb_edge_forward(const gnb_graph_t* g, int H, const float* P, int
 extern "C" int gnb_node_update(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const float* e,
                                const float* F, const float* carry, const float* h_in,
                                const float* scale_h, const float* shift_h, float* h_out, int flags,
-                               int chunk, void* stream) {
+                               int chunk, int64_t node_begin, int64_t node_end, const int32_t* xp_ptr,
+                               const int32_t* xp_row, const float* xp_buf, void* stream) {
   GNB_REQUIRE(chunk > 0, "gnb_node_update: chunk must be the carry granularity of the edge pass that filled F/carry");
   int rc = check_graph(g);
   if (rc) return rc;
-  if (g->num_nodes == 0) return 0;
+  GNB_REQUIRE(0 <= node_begin && node_begin <= node_end && node_end <= g->num_nodes, "gnb_node_update: bad node range");
+  if (node_end == node_begin) return 0;
   GNB_REQUIRE(P && h_in && scale_h && shift_h && h_out, "null pointer");
+  GNB_REQUIRE((xp_ptr == nullptr) == (xp_row == nullptr) && (xp_ptr == nullptr) == (xp_buf == nullptr),
+              "gnb_node_update: xp_ptr / xp_row / xp_buf go together");
+  GNB_REQUIRE((uintptr_t)xp_buf % 16 == 0, "gnb_node_update: xp_buf must be 16-byte aligned");
   if (g->num_edges > 0) GNB_REQUIRE(e && F && carry, "null pointer");
   GNB_REQUIRE(ldP >= ((flags & GNB_F_SYMMETRIC) ? 5 : 4) * (int64_t)H && ldP % 4 == 0, "ldP=%lld too small",
               (long long)ldP);
@@ -648,6 +669,22 @@ extern "C" int gnb_node_update(const gnb_graph_t* g, int H, const float* P, int6
                   ((uintptr_t)scale_h % 16 == 0) && ((uintptr_t)shift_h % 16 == 0),
               "pointers must be 16-byte aligned");
   GNB_DISPATCH_H(H, (node_update_impl<kH>(g, P, ldP, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk,
+                                          node_begin, node_end, xp_ptr, xp_row, xp_buf, nullptr,
+                                          (cudaStream_t)stream)));
+}
+
+extern "C" int gnb_reverse_partial(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const float* e,
+                                   int64_t node_begin, int64_t node_end, float* out, void* stream) {
+  int rc = check_graph(g);
+  if (rc) return rc;
+  GNB_REQUIRE(0 <= node_begin && node_begin <= node_end && node_end <= g->num_nodes, "gnb_reverse_partial: bad node range");
+  if (node_end == node_begin) return 0;
+  GNB_REQUIRE(P && out && (g->num_edges == 0 || e), "null pointer");
+  GNB_REQUIRE(ldP >= 4 * (int64_t)H && ldP % 4 == 0, "ldP=%lld too small", (long long)ldP);
+  GNB_REQUIRE(((uintptr_t)P % 16 == 0) && ((uintptr_t)e % 16 == 0) && ((uintptr_t)out % 16 == 0),
+              "pointers must be 16-byte aligned");
+  GNB_DISPATCH_H(H, (node_update_impl<kH>(g, P, ldP, e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                          GNB_F_SYMMETRIC, 1, node_begin, node_end, nullptr, nullptr, nullptr, out,
                                           (cudaStream_t)stream)));
 }
 

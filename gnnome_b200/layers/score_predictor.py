@@ -14,20 +14,30 @@ class ScorePredictor(nn.Module):
         self.W3 = nn.Linear(32, 1)
         self.in_features, self.hidden_edge_scores = in_features, hidden_edge_scores
 
-    def forward_positions(self, gi: GraphIndex, x, e_pos):
-        """Scores in ORIGINAL edge-id order, shape (E, 1), from position-ordered edge rows."""
+    def node_rows(self, x):
+        """S[n] = [x_n W1s^T | x_n W1d^T + b1]  ([N][2 hs]): the node halves of W1 (:13-14), once per node."""
         H, hs = self.in_features, self.hidden_edge_scores
         dev = dict(device=x.device, dtype=torch.float32)
         W1 = self.W1.weight.detach().to(**dev)                      # [hs][3H] = [W1s | W1d | W1e]
         Ws_t = torch.cat((W1[:, :H], W1[:, H:2 * H]), dim=0).t().contiguous()   # [H][2hs]
         bias = torch.cat((torch.zeros(hs, **dev), self.W1.bias.detach().to(**dev)))
-        W1e_t = W1[:, 2 * H:].t().contiguous()                      # [H][hs]
-        S = ops.node_linear(x, Ws_t, bias)
-        scores = torch.empty((gi.E, 1), **dev)
+        return ops.node_linear(x, Ws_t, bias)
+
+    def score_positions(self, gi: GraphIndex, S, e_pos, scores=None):
+        """Per-edge part: S rows of both endpoints + e W1e^T -> relu -> W2 -> relu -> W3 (:14-16)."""
+        H, hs = self.in_features, self.hidden_edge_scores
+        dev = dict(device=e_pos.device, dtype=torch.float32)
+        W1e_t = self.W1.weight.detach().to(**dev)[:, 2 * H:].t().contiguous()   # [H][hs]
+        if scores is None:
+            scores = torch.empty((gi.E, 1), **dev)
         ops.score_forward(gi, H, hs, S, W1e_t, self.W2.weight.detach().to(**dev).contiguous(),
                           self.W2.bias.detach().to(**dev), self.W3.weight.detach().to(**dev).reshape(-1).contiguous(),
                           self.W3.bias.detach().to(**dev), e_pos, scores)
         return scores
+
+    def forward_positions(self, gi: GraphIndex, x, e_pos):
+        """Scores in ORIGINAL edge-id order, shape (E, 1), from position-ordered edge rows."""
+        return self.score_positions(gi, self.node_rows(x), e_pos)
 
     def forward(self, graph, x, e):
         gi = GraphIndex.from_graph(graph)

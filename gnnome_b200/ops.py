@@ -133,13 +133,25 @@ def edge_forward_tc(gi: GraphIndex, H, P, Wp, scale_e, shift_e, e, F, carry, til
                                            current_stream_ptr(e.device)), 'gnb_edge_forward_tc')
 
 
-def node_update(gi: GraphIndex, H, P, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk):
+def node_update(gi: GraphIndex, H, P, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk,
+                node_begin=0, node_end=None, xp_ptr=None, xp_row=None, xp_buf=None):
     lib = _lib.load()
+    node_end = gi.N if node_end is None else node_end
     with _logged('gnb_node_update', h_in.device):
         _lib.check(lib.gnb_node_update(gi.ref(), H, _f32(P, 'P'), P.stride(0), _f32(e, 'e'), _f32(F, 'F'),
                                        _f32(carry, 'carry'), _f32(h_in, 'h_in'), _f32(scale_h, 'scale_h'),
                                        _f32(shift_h, 'shift_h'), _f32(h_out, 'h_out'), flags, chunk,
+                                       node_begin, node_end, _opt(xp_ptr), _opt(xp_row),
+                                       None if xp_buf is None else _f32(xp_buf, 'xp_buf'),
                                        current_stream_ptr(h_in.device)), 'gnb_node_update')
+
+
+def reverse_partial(gi: GraphIndex, H, P, e, node_begin, node_end, out):
+    """out[i - node_begin] = (sum sigma * A3h[dst] | sum sigma) over the local out-edges of node i."""
+    lib = _lib.load()
+    with _logged('gnb_reverse_partial', e.device):
+        _lib.check(lib.gnb_reverse_partial(gi.ref(), H, _f32(P, 'P'), P.stride(0), _f32(e, 'e'), node_begin, node_end,
+                                           _f32(out, 'out'), current_stream_ptr(e.device)), 'gnb_reverse_partial')
 
 
 def score_forward(gi: GraphIndex, H, hs, S, W1e_t, W2, b2, W3, b3, e, scores):
@@ -152,13 +164,16 @@ def score_forward(gi: GraphIndex, H, hs, S, W1e_t, W2, b2, W3, b3, e, scores):
 
 
 def gather_rows(x, idx, out=None):
+    """out[r] = x[idx[r]]; ``x`` may be a column block of a wider table (unit column stride)."""
     lib = _lib.load()
     rows, W = idx.numel(), x.shape[1]
     if out is None:
         out = torch.empty((rows, W), dtype=torch.float32, device=x.device)
+    if x.dtype != torch.float32 or not x.is_cuda or x.stride(1) != 1:
+        raise ValueError('x must be a float32 CUDA matrix with unit column stride')
     with _logged('gnb_gather_rows', x.device):
-        _lib.check(lib.gnb_gather_rows(_f32(x, 'x'), idx.data_ptr(), rows, W, _f32(out, 'out'),
-                                       current_stream_ptr(x.device)), 'gnb_gather_rows')
+        _lib.check(lib.gnb_gather_rows_ld(x.data_ptr(), x.stride(0), idx.data_ptr(), rows, W, _f32(out, 'out'),
+                                          out.stride(0), current_stream_ptr(x.device)), 'gnb_gather_rows_ld')
     return out
 
 

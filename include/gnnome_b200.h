@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 2
+#define GNB_ABI_VERSION 3
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -128,11 +128,25 @@ int gnb_edge_forward(const gnb_graph_t* g, int H, const float* P, int64_t ldP,
  *   Bk_i = sum_{q: src_q = i} sigmoid(e'_q) * P[dst_q][A3h] / (sum_q sigmoid(e'_q) + 1e-6)   (symmetric only)
  *   h'_i = relu((P[i][A1h] + F_i + Bk_i) * scale_h + shift_h) (+ h_i if GNB_F_RESIDUAL)
  * chunk = carry granularity of the edge pass that produced F / carry (gnb_edge_chunk or gnb_edge_chunk_tc).
+ * Only nodes node_begin <= i < node_end are updated (single GPU: 0, num_nodes; h_in / h_out need rows
+ * for those nodes only).  Multi-GPU (graph partitioned by destination range, the staged graph holds the
+ * owned nodes followed by halo source nodes): xp_ptr[i] .. xp_ptr[i+1] index xp_row, whose entries are
+ * rows of xp_buf[.][2H] = (num | den) partial sums that OTHER ranks computed for node i with
+ * gnb_reverse_partial; they are added, in that order, before the division.  Pass NULLs when unused.
  * Dropout (gated_gcn_full.py:139) is left to the caller (torch RNG semantics). */
 int gnb_node_update(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const float* e,
                     const float* F, const float* carry, const float* h_in,
                     const float* scale_h, const float* shift_h, float* h_out, int flags,
-                    int chunk, void* stream);
+                    int chunk, int64_t node_begin, int64_t node_end, const int32_t* xp_ptr,
+                    const int32_t* xp_row, const float* xp_buf, void* stream);
+
+/* The un-normalised halves of the reverse aggregation (gated_gcn_full.py:125-126) for the nodes
+ * node_begin <= i < node_end of the staged (local) graph:
+ *   out[i - node_begin][0:H]  = sum_{q: src_q = i} sigmoid(e'_q) * P[dst_q][A3h]
+ *   out[i - node_begin][H:2H] = sum_{q: src_q = i} sigmoid(e'_q)
+ * Used for halo source nodes, whose owner rank finishes the sum (gnb_node_update xp_*). */
+int gnb_reverse_partial(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const float* e,
+                        int64_t node_begin, int64_t node_end, float* out, void* stream);
 
 /* ScorePredictor (score_predictor.py:12-24) with W1 = [W1s | W1d | W1e] split so that the node
  * halves are projected once per node:  S[n] = [x_n * W1s^T | x_n * W1d^T + b1]  ([N][2*hs], from
@@ -148,6 +162,10 @@ int gnb_score_forward(const gnb_graph_t* g, int H, int hs, const float* S, const
  * position order for the layer-level API. */
 int gnb_gather_rows(const float* in, const int32_t* idx, int64_t rows, int W, float* out,
                     void* stream);
+/* Same with explicit row strides (in floats, multiples of 4): packs W columns of selected rows of a wider
+ * table, e.g. the (B1h, A2h) block of the node table for the multi-GPU halo exchange. */
+int gnb_gather_rows_ld(const float* in, int64_t ld_in, const int32_t* idx, int64_t rows, int W,
+                       float* out, int64_t ld_out, void* stream);
 /* out[idx[r]][0:W] = in[r][0:W] */
 int gnb_scatter_rows(const float* in, const int32_t* idx, int64_t rows, int W, float* out,
                      void* stream);
