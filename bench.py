@@ -252,7 +252,8 @@ def run_gpu_arm(args, wl):
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     peak, peak_src = measured_peak()
-    ek_name = 'gnb_edge_forward_tc' if 'gnb_edge_forward_tc' in ktimes else 'gnb_edge_forward'
+    ek_name = next((k for k in ('gnb_edge_forward_tc2', 'gnb_edge_forward_tc', 'gnb_edge_forward') if k in ktimes),
+                   'gnb_edge_forward')
     ek = ktimes.get(ek_name, [])
     roofline = None
     if ek:
@@ -311,7 +312,7 @@ def run_gpu_arm(args, wl):
     line = {
         'metric': 'edges/s', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if world > 1 else 'weak',
-        'vs_baseline': None, 'dtype': 'f32 state, fp16x2-split tensor-core products with f32 accumulate', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': 'f32 (state held as split fp16 hi+lo pairs, 22 significant bits; fp16x2-split tcgen05 products, f32 accumulate)', 'data': 'synthetic',
         'config': {'workload': desc, 'N': n, 'E': m, 'H': H, 'L': L, 'model': 'SymGatedGCNModel eval, seed-0 init',
                    'graph': 'make_assembly_graph(seed=0, band=64, alpha=2.2, p_long=0.01)',
                    'l2': 'inputs (>= 1 GB of edge state per layer) exceed the 126 MB L2; no flush needed',

@@ -46,12 +46,22 @@ SIGNATURES = {
     'gnb_edge_tile_tc': (_I, [_I]),
     'gnb_edge_forward_tc': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     'gnb_score_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'gnb_split16_bytes': (_S, [_L, _I]),
+    'gnb_split_rows': (_I, [_P, _P, _L, _I, _P, _P]),
+    'gnb_merge_rows': (_I, [_P, _P, _L, _I, _P, _P]),
+    'gnb_encode2': (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'gnb_node_linear_tc2': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
+    'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    'gnb_node_update2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),
+    'gnb_reverse_partial2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _L, _L, _P, _P]),
+    'gnb_score_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'gnb_score_forward2': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'gnb_gather_rows': (_I, [_P, _P, _L, _I, _P, _P]),
     'gnb_gather_rows_ld': (_I, [_P, _L, _P, _L, _I, _P, _L, _P]),
     'gnb_scatter_rows': (_I, [_P, _P, _L, _I, _P, _P]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 

@@ -6,6 +6,8 @@
 // accumulators and segment boundaries are group-uniform branches -- no atomics, no shuffles, and a
 // bit-reproducible summation order (position order).  Gathers of node-table rows are 128-byte
 // coalesced per warp (32 consecutive channels of one row).
+#include <cuda_fp16.h>
+
 #include "gnb_common.cuh"
 
 namespace gnb {
@@ -414,7 +416,8 @@ struct ScoreCfg {
       ((size_t)R * H + 16 * HS + (size_t)R * HS + (size_t)R * TS + 32 * TS + 32 + 32) * 4 + (size_t)3 * R * 4;
 };
 
-template <int H, int HS>
+// kSplit16: e points at the split16 images of the edge state (fp16 hi [E][H], then lo [E][H]; x = 16 * (hi + lo))
+template <int H, int HS, bool kSplit16>
 __global__ void __launch_bounds__(kThreads)
 score_forward_kernel(gnb_graph_t g, const float* __restrict__ S, const float* __restrict__ W1e_t,
                      const float* __restrict__ W2, const float* __restrict__ b2,
@@ -449,7 +452,21 @@ score_forward_kernel(gnb_graph_t g, const float* __restrict__ S, const float* __
     for (int i = threadIdx.x; i < C::R * (H / 4); i += kThreads) {
       int row = i / (H / 4), q4 = i - row * (H / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p0 + row < E) v = *reinterpret_cast<const float4*>(e + (p0 + row) * H + q4 * 4);
+      if (p0 + row < E) {
+        if (kSplit16) {
+          const __half* e_hi = reinterpret_cast<const __half*>(e);
+          const __half* e_lo = e_hi + E * H;
+          const uint2 hh = *reinterpret_cast<const uint2*>(e_hi + (p0 + row) * H + q4 * 4);
+          const uint2 ll = *reinterpret_cast<const uint2*>(e_lo + (p0 + row) * H + q4 * 4);
+          const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hh.x));
+          const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&hh.y));
+          const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ll.x));
+          const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&ll.y));
+          v = make_float4((h0.x + l0.x) * 16.f, (h0.y + l0.y) * 16.f, (h1.x + l1.x) * 16.f, (h1.y + l1.y) * 16.f);
+        } else {
+          v = *reinterpret_cast<const float4*>(e + (p0 + row) * H + q4 * 4);
+        }
+      }
       *reinterpret_cast<float4*>(e_s + row * H + q4 * 4) = v;
     }
     for (int row = threadIdx.x; row < C::R; row += kThreads) {
@@ -548,28 +565,28 @@ static int node_update_impl(const gnb_graph_t* g, const float* P, int64_t ldP, c
   return check_launch(partial_out ? "gnb_reverse_partial" : "gnb_node_update");
 }
 
-template <int H, int HS>
+template <int H, int HS, bool kSplit16>
 static int score_forward_impl(const gnb_graph_t* g, const float* S, const float* W1e_t, const float* W2,
                               const float* b2, const float* W3, const float* b3, const float* e,
                               float* scores, cudaStream_t stream) {
   using C = ScoreCfg<H, HS>;
   int bps = 0;
-  int rc = launch_cfg(score_forward_kernel<H, HS>, C::smem_bytes, &bps);
+  int rc = launch_cfg(score_forward_kernel<H, HS, kSplit16>, C::smem_bytes, &bps);
   if (rc) return rc;
   int64_t tiles = (g->num_edges + C::R - 1) / C::R;
-  score_forward_kernel<H, HS><<<grid_for(tiles, bps), kThreads, C::smem_bytes, stream>>>(
+  score_forward_kernel<H, HS, kSplit16><<<grid_for(tiles, bps), kThreads, C::smem_bytes, stream>>>(
       *g, S, W1e_t, W2, b2, W3, b3, e, scores);
   return check_launch("gnb_score_forward");
 }
 
-template <int H>
+template <int H, bool kSplit16 = false>
 static int score_forward_hs(int hs, const gnb_graph_t* g, const float* S, const float* W1e_t,
                             const float* W2, const float* b2, const float* W3, const float* b3,
                             const float* e, float* scores, cudaStream_t stream) {
   switch (hs) {
-    case 32: return score_forward_impl<H, 32>(g, S, W1e_t, W2, b2, W3, b3, e, scores, stream);
-    case 64: return score_forward_impl<H, 64>(g, S, W1e_t, W2, b2, W3, b3, e, scores, stream);
-    case 128: return score_forward_impl<H, 128>(g, S, W1e_t, W2, b2, W3, b3, e, scores, stream);
+    case 32: return score_forward_impl<H, 32, kSplit16>(g, S, W1e_t, W2, b2, W3, b3, e, scores, stream);
+    case 64: return score_forward_impl<H, 64, kSplit16>(g, S, W1e_t, W2, b2, W3, b3, e, scores, stream);
+    case 128: return score_forward_impl<H, 128, kSplit16>(g, S, W1e_t, W2, b2, W3, b3, e, scores, stream);
   }
   set_error("hidden_edge_scores=%d unsupported (32, 64, 128)", hs);
   return GNB_E_INVALID;
@@ -697,4 +714,16 @@ extern "C" int gnb_score_forward(const gnb_graph_t* g, int H, int hs, const floa
   GNB_REQUIRE(S && W1e_t && W2 && b2 && W3 && b3 && e && scores, "null pointer");
   GNB_REQUIRE(((uintptr_t)e % 16 == 0) && ((uintptr_t)W1e_t % 16 == 0), "pointers must be 16-byte aligned");
   GNB_DISPATCH_H(H, (score_forward_hs<kH>(hs, g, S, W1e_t, W2, b2, W3, b3, e, scores, (cudaStream_t)stream)));
+}
+
+extern "C" int gnb_score_forward2(const gnb_graph_t* g, int H, int hs, const float* S, const float* W1e_t,
+                                  const float* W2, const float* b2, const float* W3, const float* b3,
+                                  const void* e16, float* scores, void* stream) {
+  int rc = check_graph(g);
+  if (rc) return rc;
+  if (g->num_edges == 0) return 0;
+  GNB_REQUIRE(S && W1e_t && W2 && b2 && W3 && b3 && e16 && scores, "null pointer");
+  GNB_REQUIRE(((uintptr_t)e16 % 16 == 0) && ((uintptr_t)W1e_t % 16 == 0), "pointers must be 16-byte aligned");
+  GNB_DISPATCH_H(H, (score_forward_hs<kH, true>(hs, g, S, W1e_t, W2, b2, W3, b3, (const float*)e16, scores,
+                                               (cudaStream_t)stream)));
 }

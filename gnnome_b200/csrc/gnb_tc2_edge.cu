@@ -1,0 +1,401 @@
+// Fused edge pass of one (Sym)GatedGCN layer, second generation: TMA-fed tcgen05 with the edge state held in the
+// split16 format (gnb_tma.cuh).  Reference layers/gated_gcn_full.py:97,104-114:
+//   z_p  = B1h[src_p] + B2h[dst_p] + e_p * W_B3^T         (E x H x H product on tcgen05, fp16 hi/lo split, fp32 in TMEM)
+//   e'_p = relu(z_p * scale + shift) (+ e_p)               written over e in place
+//   F_i  = sum_{p: dst_p = i} sigmoid(e'_p) * A2h[src_p] / (sum_p sigmoid(e'_p) + 1e-6)
+//
+// Persistent CTAs, one per SM; a CTA owns HC = min(H, 128) output channels (H = 256: the two channel halves of a
+// tile run on neighbouring CTAs) with its W_B3 block resident in TMEM, and walks 64-edge tiles of the dst-sorted
+// edge array.  One shared-memory stage serves a tile through its whole life:
+//   TMA load (hi, lo images, 128B-swizzled)  ->  MMA B operand  ->  residual source for the epilogue  ->
+//   e' written over it in place (same thread, same address)  ->  TMA store back to HBM.
+//   warp 0      : producer: TMA loads (lane 0) + the tile's (src, dst) indices into the stage's index area
+//   warp 1      : MMA issue (one lane)
+//   warps 2, 3  : TMA store of group 0 / 1 (wait for the group's epilogue, H = 256: for the other channel half
+//                 to have loaded the tile, store, release the stage)
+//   warps 4..19 : epilogue, 2 groups (= accumulator buffers) x 4 TMEM lane quarters x 2 chunks of 32 edges.
+//                 A thread owns ONE channel and walks its 32 consecutive edges: gathers of the (B1h, A2h) node
+//                 rows are coalesced across the warp, per-destination sums are register accumulators closed at
+//                 warp-uniform segment boundaries (no atomics, fixed summation order).  Segments that straddle
+//                 a 32-edge chunk leave partial sums in carry[chunk][4][H], resolved by gnb_node_update2.
+#include <type_traits>
+
+#include "gnb_tma.cuh"
+
+namespace gnb {
+namespace tc {
+
+constexpr int kE2NT = 64;        // edges per tile (MMA N)
+constexpr int kE2Chunk = 32;     // edges per epilogue warp = carry granularity
+constexpr int kE2Groups = 2;     // epilogue groups = accumulator buffers
+constexpr int kE2FirstEpiWarp = 4;
+constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 8 * kE2Groups);
+constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[64], dst[64], prev_dst, next_dst
+
+template <int H>
+struct Edge2Cfg {
+  static constexpr int HC = H < kM ? H : kM;   // live channels per CTA
+  static constexpr int NH = H / HC;            // channel halves (CTAs per tile)
+  using T = Tile2<H, kE2NT>;
+  // NB <= 2 * groups: an epilogue group can never run two tiles ahead of its store warp (see sfull)
+  static constexpr int NB = (H >= 256) ? 3 : 4;
+  // epilogue warps of a group that own live channels (the others idle: they must not feed the barriers, or they
+  // would run ahead of the live ones and complete a phase early)
+  static constexpr int LIVE_WARPS = 2 * (HC / 32);
+  static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + kE2Groups * kE2NT);
+  static constexpr uint32_t D_COL0 = 2 * T::W_COLS;
+  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 256;
+};
+
+__device__ __forceinline__ void red_release_add2(int32_t* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire2(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint16_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+template <int H>
+__global__ void __launch_bounds__(kE2Threads, 1)
+edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                        gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ Wp,
+                        const float* __restrict__ scale_e, const float* __restrict__ shift_e,
+                        float* __restrict__ F, float* __restrict__ carry, int32_t* tile_flags, int epoch, int flags,
+                        int workers) {
+  using C = Edge2Cfg<H>;
+  using T = typename C::T;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* bufs = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  int* idx_area = reinterpret_cast<int*>(bufs + (size_t)C::NB * T::BUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_area + C::NB * kE2IdxInts);
+  uint64_t* full = bars;                    // [NB] producer (TMA bytes + 32 index lanes) -> MMA, epilogue
+  uint64_t* empty = full + C::NB;           // [NB] store warp -> producer
+  uint64_t* dfull = empty + C::NB;          // [G]  MMA -> epilogue
+  uint64_t* dempty = dfull + kE2Groups;     // [G]  epilogue -> MMA
+  uint64_t* sfull = dempty + kE2Groups;     // [G]  epilogue (e' written into the stage) -> store warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + kE2Groups);
+
+  const int half = blockIdx.x % C::NH, worker = blockIdx.x / C::NH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t E = g.num_edges;
+  const int64_t num_tiles = (E + kE2NT - 1) / kE2NT;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::NB; ++i) {
+      mbar_init(&full[i], 33);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kE2Groups; ++i) {
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], C::LIVE_WARPS);
+      mbar_init(&sfull[i], C::LIVE_WARPS);
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&map_hi);
+    prefetch_tensormap(&map_lo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= kE2FirstEpiWarp && warp < kE2FirstEpiWarp + 4)
+    load_weights_to_tmem<H>(Wp + (size_t)half * 2 * kM * H, tmem_base, warp & 3, lane);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: TMA + indices
+    auto load_idx = [&](int64_t t, int (&r)[5]) {
+      const int64_t p0 = t * kE2NT + lane, p1 = p0 + 32;
+      r[0] = (p0 < E) ? g.in_src[p0] : 0;
+      r[1] = (p1 < E) ? g.in_src[p1] : 0;
+      r[2] = (p0 < E) ? g.in_dst[p0] : -1;
+      r[3] = (p1 < E) ? g.in_dst[p1] : -1;
+      r[4] = -1;
+      if (lane == 0 && t > 0) r[4] = g.in_dst[t * kE2NT - 1];
+      if (lane == 1 && (t + 1) * kE2NT < E) r[4] = g.in_dst[(t + 1) * kE2NT];
+    };
+    int cur[5], nxt[5];
+    if (worker < num_tiles) load_idx(worker, cur);
+    int i = 0;
+    for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
+      const int s = i % C::NB;
+      mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1);
+      if (lane == 0) {
+        uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
+        mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < T::KBLOCKS; ++kb) {
+          tma_load_2d(stage + kb * T::KB_BYTES, &map_hi, kb * kKB, (int)(t * kE2NT), &full[s]);
+          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_lo, kb * kKB, (int)(t * kE2NT), &full[s]);
+        }
+      }
+      if (t + workers < num_tiles) load_idx(t + workers, nxt);   // in flight while this tile's indices are published
+      int* ia = idx_area + s * kE2IdxInts;
+      ia[lane] = cur[0];
+      ia[32 + lane] = cur[1];
+      ia[kE2NT + lane] = cur[2];
+      ia[kE2NT + 32 + lane] = cur[3];
+      if (lane < 2) ia[2 * kE2NT + lane] = cur[4];
+      mbar_arrive(&full[s]);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cur[k] = nxt[k];
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issue
+    int i = 0;
+    for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
+      const int s = i % C::NB, d = i % kE2Groups;
+      mbar_wait(&full[s], (i / C::NB) & 1);
+      // both channel halves read whole rows of e and overwrite their own half in place: tell the other half
+      // that this CTA's copy of tile t has left global memory
+      if (C::NH > 1 && lane == 0) red_release_add2(tile_flags + t, 1);
+      mbar_wait(&dempty[d], ((i / kE2Groups) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_tile_mma_sw128<H, kE2NT>(tmem_base, tmem_base + C::D_COL0 + d * kE2NT,
+                                       smem_u32(bufs + (size_t)s * T::BUF_BYTES));
+        mma_commit(&dfull[d]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < kE2FirstEpiWarp) {
+    // ---------------------------------------------------------------- TMA store of one epilogue group
+    const int grp = warp - 2;
+    if (lane == 0) {
+      int i = 0, j = 0;
+      for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
+        if (i % kE2Groups != grp) continue;
+        const int s = i % C::NB;
+        mbar_wait(&sfull[grp], j & 1);
+        ++j;
+        if (C::NH > 1) {  // the other half must have read tile t before our channels of it are overwritten
+          while (ld_acquire2(tile_flags + t) < C::NH * epoch) __nanosleep(32);
+        }
+        const uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
+#pragma unroll
+        for (int kbl = 0; kbl < C::HC / kKB; ++kbl) {
+          const int kb = half * (C::HC / kKB) + kbl;
+          tma_store_2d(&map_hi, stage + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
+          tma_store_2d(&map_lo, stage + T::IMG_BYTES + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
+        }
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&empty[s]);
+      }
+      tma_store_wait_all();
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int ew = warp - kE2FirstEpiWarp;
+    const int grp = ew >> 3, sub = (ew >> 2) & 1, q = warp & 3;
+    const int cl = q * 32 + lane;            // TMEM lane = channel within the CTA's block
+    const bool ch_ok = cl < C::HC;           // warp-uniform (HC is a multiple of 32)
+    const int c = half * C::HC + (ch_ok ? cl : 0);
+    const int64_t my_tiles = ch_ok ? num_tiles : 0;   // warps without live channels (H = 64) sit the loop out
+    const float sc = scale_e[c], sh = shift_e[c];
+    const bool residual = flags & GNB_F_RESIDUAL;
+    const float* Pc = P + 2 * c;             // (B1h[c], A2h[c]) interleaved
+    const float* Pb2 = P + 2 * H + c;        // B2h[c]
+    constexpr unsigned kFull = 0xffffffffu;
+    // this thread's column of the stage: element (row, c) of an image sits at
+    //   (c / 64) * KB_BYTES + row * 128 + ((((c % 64) / 8) ^ (row % 8)) * 16) + (c % 8) * 2
+    const uint32_t col_base = (uint32_t)((c >> 6) * T::KB_BYTES + sub * kE2Chunk * 128 + ((c & 7) << 1));
+    const uint32_t col_x = (uint32_t)((c & 63) >> 3);
+    int i = 0;
+    for (int64_t t = worker; t < my_tiles; t += workers, ++i) {
+      if (i % kE2Groups != grp) continue;
+      const int s = i % C::NB;
+      const int64_t cs = t * kE2NT + sub * kE2Chunk;
+      const bool live = cs < E;              // warp-uniform; false only for the second half of a ragged last tile
+      const int n = live ? (int)((E - cs < kE2Chunk) ? (E - cs) : kE2Chunk) : 0;
+      mbar_wait(&full[s], (i / C::NB) & 1);  // indices published (and the operand tile has landed)
+      if (!live) {  // nothing to compute, but the barriers still have to be fed
+        mbar_wait(&dfull[grp], (i / kE2Groups) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&dempty[grp]);
+          mbar_arrive(&sfull[grp]);
+        }
+        continue;
+      }
+      const int* ia = idx_area + s * kE2IdxInts;
+      const int my_src = ia[sub * kE2Chunk + lane];
+      const int my_dst = ia[kE2NT + sub * kE2Chunk + lane];
+      const int prev_dst = (sub == 0) ? ia[2 * kE2NT] : ia[kE2NT + kE2Chunk - 1];
+      const int next_dst = (sub == 0) ? ia[kE2NT + kE2Chunk] : ia[2 * kE2NT + 1];
+      int head_dst = -1, tail_dst = -1;
+      const int up = __shfl_up_sync(kFull, my_dst, 1);
+      // bit j: edge j of the chunk opens a new destination segment
+      const unsigned segmask = __ballot_sync(kFull, lane == 0 || (lane < n && my_dst != up));
+      const int first_dst = __shfl_sync(kFull, my_dst, 0);
+      const int last_dst = __shfl_sync(kFull, my_dst, n - 1);
+      if (prev_dst == first_dst) head_dst = first_dst;
+      if (next_dst == last_dst) tail_dst = last_dst;
+
+      const int64_t chunk = cs / kE2Chunk;
+      const uint32_t st_hi = smem_u32(bufs + (size_t)s * T::BUF_BYTES) + col_base;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + grp * kE2NT + sub * kE2Chunk;
+      int cur = -1;
+      float num = 0.f, den = 0.f, b2s = 0.f;
+
+      // Software pipeline over four batches of eight edges: the gathers of batch b+1 are in flight while batch b
+      // is computed.  fa = (B1h, A2h)[src], fb = B2h[dst] (fetched only where a destination segment opens).
+      constexpr int kEB = 8;
+      float2 ba[2][kEB];
+      float b2v[2][kEB];
+      auto fetch = [&](int b, float2 (&fa)[kEB], float (&fb)[kEB]) {
+        const unsigned mb = segmask >> (b * kEB);
+#pragma unroll
+        for (int u = 0; u < kEB; ++u) {
+          const int sj = __shfl_sync(kFull, my_src, b * kEB + u);
+          fa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj * ldP));
+          fb[u] = 0.f;
+          if (mb & (1u << u)) {   // warp-uniform
+            const int dj = __shfl_sync(kFull, my_dst, b * kEB + u);
+            fb[u] = __ldg(Pb2 + (int64_t)dj * ldP);
+          }
+        }
+      };
+      auto compute = [&](int b, const float2 (&fa)[kEB], const float (&fb)[kEB]) {
+        uint32_t zr[kEB];
+        tmem_ld8(taddr + b * kEB, zr);
+        tmem_ld_wait();
+        if (b == kE2Chunk / kEB - 1) {   // last read of this accumulator buffer: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dempty[grp]);
+        }
+        const unsigned mb = segmask >> (b * kEB);
+#pragma unroll
+        for (int u = 0; u < kEB; ++u) {
+          if (mb & (1u << u)) {          // warp-uniform: close the running segment, open the next
+            if (cur >= 0) {
+              if (cur == head_dst) {
+                carry[(chunk * 4 + 0) * H + c] = num;
+                carry[(chunk * 4 + 1) * H + c] = den;
+              } else {
+                F[(int64_t)cur * H + c] = gate_div(num, den);
+              }
+            }
+            cur = __shfl_sync(kFull, my_dst, b * kEB + u);
+            num = 0.f;
+            den = 0.f;
+            b2s = fmaf(fb[u], sc, sh);
+          }
+          // row b*8+u of the chunk: row % 8 == u
+          const uint32_t a_hi = st_hi + (uint32_t)((b * kEB + u) * 128) + ((col_x ^ (uint32_t)u) << 4);
+          const uint32_t a_lo = a_hi + T::IMG_BYTES;
+          float v = fmaf(__uint_as_float(zr[u]) + fa[u].x, sc, b2s);
+          v = fmaxf(v, 0.f);
+          if (residual) {
+            const __half_raw hr{lds_u16(a_hi)}, lr{lds_u16(a_lo)};
+            v += (__half2float(__half(hr)) + __half2float(__half(lr))) * kWScale;
+          }
+          if (b * kEB + u < n) {
+            __half nh, nl;
+            split1(v, nh, nl);
+            sts_u16(a_hi, __half_raw(nh).x);
+            sts_u16(a_lo, __half_raw(nl).x);
+            const float sg = sigmoidf_fast(v);
+            num = fmaf(sg, fa[u].y, num);
+            den += sg;
+          }
+        }
+      };
+      fetch(0, ba[0], b2v[0]);
+      mbar_wait(&dfull[grp], (i / kE2Groups) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < kE2Chunk / kEB; b += 2) {
+        fetch(b + 1, ba[1], b2v[1]);
+        compute(b, ba[0], b2v[0]);
+        if (b + 2 < kE2Chunk / kEB) fetch(b + 2, ba[0], b2v[0]);
+        compute(b + 1, ba[1], b2v[1]);
+      }
+      // close the segment that is still open at the end of the chunk
+      if (cur == tail_dst) {
+        carry[(chunk * 4 + 2) * H + c] = num;
+        carry[(chunk * 4 + 3) * H + c] = den;
+      } else if (cur == head_dst) {
+        carry[(chunk * 4 + 0) * H + c] = num;
+        carry[(chunk * 4 + 1) * H + c] = den;
+      } else {
+        F[(int64_t)cur * H + c] = gate_div(num, den);
+      }
+      // e' is in the stage: make it visible to the async proxy, then hand the stage to the store warp
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull[grp]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int H>
+static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t ldP, const void* Wp,
+                                 const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
+                                 int32_t* tile_flags, int epoch, int flags, cudaStream_t stream) {
+  using C = Edge2Cfg<H>;
+  cudaError_t err = cudaFuncSetAttribute(edge_forward_tc2_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM);
+  if (err != cudaSuccess) {
+    set_error("gnb_edge_forward_tc2: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(err));
+    return (int)err;
+  }
+  if (C::NH > 1) GNB_REQUIRE(tile_flags != nullptr && epoch > 0, "gnb_edge_forward_tc2: H=%d needs tile_flags and epoch >= 1", H);
+  const int64_t E = g->num_edges;
+  CUtensorMap map_hi, map_lo;
+  int rc = make_image_map(&map_hi, e16, E, H, kE2NT);
+  if (rc) return rc;
+  rc = make_image_map(&map_lo, (const __half*)e16 + E * H, E, H, kE2NT);
+  if (rc) return rc;
+  const int64_t num_tiles = (E + kE2NT - 1) / kE2NT;
+  int workers = sm_count() / C::NH;
+  if (workers > num_tiles) workers = (int)num_tiles;
+  // every CTA must be resident at the same time (the channel halves wait on each other's flags)
+  edge_forward_tc2_kernel<H><<<workers * C::NH, kE2Threads, C::SMEM, stream>>>(
+      map_hi, map_lo, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, tile_flags, epoch, flags, workers);
+  return check_launch("gnb_edge_forward_tc2");
+}
+
+}  // namespace tc
+}  // namespace gnb
+
+using namespace gnb;
+
+extern "C" int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
+                                    const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
+                                    int32_t* tile_flags, int epoch, int flags, void* stream) {
+  GNB_REQUIRE(g != nullptr && g->num_edges >= 0 && g->in_ptr != nullptr, "graph not staged");
+  if (g->num_edges == 0) return 0;
+  GNB_REQUIRE(g->in_src && g->in_dst, "graph not staged");
+  GNB_REQUIRE(P && Wp && scale_e && shift_e && e16 && F && carry, "null pointer");
+  GNB_REQUIRE(ldP >= ((flags & GNB_F_SYMMETRIC) ? 5 : 4) * (int64_t)H && ldP % 2 == 0, "ldP=%lld too small",
+              (long long)ldP);
+  GNB_REQUIRE(((uintptr_t)P % 8 == 0) && ((uintptr_t)e16 % 16 == 0) && ((uintptr_t)Wp % 16 == 0),
+              "gnb_edge_forward_tc2: e16 must be 16-byte aligned, P 8-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (H) {
+    case 64: return tc::edge_forward_tc2_impl<64>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags, s);
+    case 128: return tc::edge_forward_tc2_impl<128>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags, s);
+    case 256: return tc::edge_forward_tc2_impl<256>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags, s);
+  }
+  set_error("gnb_edge_forward_tc2: hidden_features=%d unsupported (64, 128, 256)", H);
+  return GNB_E_INVALID;
+}

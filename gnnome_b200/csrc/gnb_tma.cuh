@@ -1,0 +1,123 @@
+// TMA (cp.async.bulk.tensor) + 128-byte-swizzled operand tiles for the second-generation tensor-core kernels.
+//
+// State layout in HBM ("split16"): a matrix X[rows][K] of fp32 values is held as TWO row-major fp16 images,
+//   hi[r][k] = fp16(x / 16),  lo[r][k] = fp16(x / 16 - hi[r][k])           (x ~ 16 * (hi + lo), 22 significant bits)
+// at base and base + rows * K halves.  It is the same 4 bytes per element as fp32, but the images ARE the
+// tcgen05 operands: a tile of NT rows is brought into shared memory by the TMA engine (no conversion
+// instructions, no registers in flight), one [NT rows][64 halves = 128 bytes] box per 64-channel block and
+// image, written in the SWIZZLE_128B pattern the UMMA shared-memory descriptor expects, and e' / h' go back
+// with TMA stores from the same shared-memory tile.
+#pragma once
+
+#include <cuda.h>
+
+#include "gnb_tc.cuh"
+
+namespace gnb {
+namespace tc {
+
+constexpr int kKB = 64;                       // halves per 128-byte swizzle row (one "k block")
+
+// Bytes of one k block of an NT-row tile, and of one whole stage (both images, K / 64 k blocks each).
+template <int K, int NT>
+struct Tile2 {
+  static constexpr int KBLOCKS = K / kKB;
+  static constexpr int KB_BYTES = NT * 128;
+  static constexpr int IMG_BYTES = KBLOCKS * KB_BYTES;
+  static constexpr int BUF_BYTES = 2 * IMG_BYTES;
+  static constexpr int W_COLS = K / 2;
+  static constexpr int KSTEPS = K / 16;
+  static_assert(K % kKB == 0 && NT % 8 == 0, "tile shape");
+};
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+// 2-D tensor map over one fp16 image [rows][K] (row-major), box = [box_rows][64 halves], SWIZZLE_128B,
+// out-of-bounds rows read as zeros (loads) / are clipped (stores).  Returns 0 or a negative GNB_E_* code.
+int make_image_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows);
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// global -> shared, completion counted on an mbarrier (x = element index along K, y = row)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared -> global, tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of every committed store has been read (the tile may be reused)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major, SWIZZLE_128B operand: rows are 128 bytes apart, 8-row swizzle
+// atoms 1024 bytes apart (SBO); LBO is not used by swizzled K-major layouts (set to 1).  `addr` must lie in a
+// 1024-byte aligned tile; advancing K by 16 halves = +32 bytes on the start address.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+// Byte offset of element (row r, channel k) inside one image of a stage laid out by tma_load_2d.
+template <int NT>
+__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
+  const int kb = k >> 6, kk = k & 63;
+  return (uint32_t)(kb * (NT * 128) + r * 128 + ((((kk >> 3) ^ (r & 7)) << 4) | ((kk & 7) << 1)));
+}
+
+// The three split-precision products of one tile: D (+)= Whi*Xhi + Whi*Xlo + Wlo*Xhi (small terms first).
+// tmem_w: first column of the W_hi image (W_lo at + K/2); b_addr: shared address of the stage.
+template <int K, int NT>
+__device__ __forceinline__ void issue_tile_mma_sw128(uint32_t tmem_w, uint32_t tmem_d, uint32_t b_addr) {
+  using T = Tile2<K, NT>;
+  constexpr uint32_t idesc = make_idesc(kM, NT);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {  // Wlo*Xhi, Whi*Xlo, Whi*Xhi
+    const uint32_t a0 = tmem_w + (term == 0 ? T::W_COLS : 0);
+    const uint32_t b0 = b_addr + (term == 1 ? T::IMG_BYTES : 0);
+#pragma unroll
+    for (int ks = 0; ks < T::KSTEPS; ++ks) {
+      const uint32_t baddr = b0 + (ks >> 2) * T::KB_BYTES + (ks & 3) * 32;
+      mma_ts_f16(tmem_d, a0 + ks * 8, make_sw128_desc(baddr), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// x (fp32) -> the two fp16 halves of the split16 format
+__device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
+  const float xs = x * kXScale;
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
+}
+__device__ __forceinline__ float merge1(__half hi, __half lo) {
+  return (__half2float(hi) + __half2float(lo)) * kWScale;   // kWScale == 1 / kXScale == 16
+}
+
+}  // namespace tc
+}  // namespace gnb

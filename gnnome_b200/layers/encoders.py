@@ -11,6 +11,14 @@ def encode_rows(x, idx, lin1, lin2, rows):
                       lin2.weight.detach().to(**dev).t().contiguous(), lin2.bias.detach().to(**dev), rows)
 
 
+def encode_rows2(x, idx, lin1, lin2, rows, want16=True, want32=False):
+    """Encoder output as split16 images and / or fp32 rows: ``(out16, out32)``."""
+    dev = dict(device=x.device, dtype=torch.float32)
+    return ops.encode2(x, idx, lin1.weight.detach().to(**dev).contiguous(), lin1.bias.detach().to(**dev),
+                       lin2.weight.detach().to(**dev).t().contiguous(), lin2.bias.detach().to(**dev), rows,
+                       want16=want16, want32=want32)
+
+
 class _Encoder(nn.Module):
     def __init__(self, in_channels, hidden_channels, out_channels, bias=True):
         super().__init__()

@@ -13,20 +13,35 @@ from .. import _lib, ops
 from ..graph import GraphIndex
 
 
-_BACKEND = 'tc'
+_BACKEND = 'tc2'
+_SPLIT16_WIDTHS = (64, 128, 256)
 
 
 def set_backend(name):
-    """'tc' (default): dense products on the tcgen05 tensor cores (fp16 hi/lo split, fp32 accumulate);
+    """'tc2' (default): TMA-fed tcgen05 kernels with the state held as split fp16 (hi, lo) images
+    (hidden_features 64 / 128 / 256; other widths fall back to 'tc');
+    'tc': first-generation tcgen05 kernels, fp32 state converted on the fly by producer warps;
     'ffma': the CUDA-core fp32 kernels (bring-up path, kept as an on-device cross-check)."""
     global _BACKEND
-    if name not in ('tc', 'ffma'):
+    if name not in ('tc2', 'tc', 'ffma'):
         raise ValueError(name)
     _BACKEND = name
 
 
 def get_backend():
     return _BACKEND
+
+
+def effective_backend(H):
+    """The kernel family that actually runs a layer of width H under the current backend."""
+    if _BACKEND == 'tc2':
+        return 'tc2' if H in _SPLIT16_WIDTHS else 'tc'
+    return _BACKEND
+
+
+def state_format(H):
+    """'split16' (fp16 hi/lo images, gnb_tma.cuh) or 'fp32' rows: how h / e are held between kernels."""
+    return 'split16' if effective_backend(H) == 'tc2' else 'fp32'
 
 
 def _bn_affine(norm, device):
@@ -71,7 +86,7 @@ class _GatedGCNBase(nn.Module):
         """Kernel-side views of the parameters (see _pack_now), cached until a parameter / buffer
         changes (torch bumps ``_version`` on every in-place update) or moves."""
         key = tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers()))
-        key += (str(device), _BACKEND)
+        key += (str(device), effective_backend(self.out_channels))
         cache = self.__dict__.get('_pack_cache')
         if cache is None or cache[0] != key:
             cache = self.__dict__['_pack_cache'] = (key, self._pack_now(device))
@@ -93,7 +108,7 @@ class _GatedGCNBase(nn.Module):
         blocks_b.append(b(self.A_1))
         Wn = torch.cat(blocks_w, dim=0).contiguous()                 # [5H or 4H][H_in] (nn.Linear layout)
         bn = torch.cat(blocks_b, dim=0).contiguous()
-        if _BACKEND == 'tc':
+        if effective_backend(H) in ('tc', 'tc2'):
             Wn_t, We_t = ops.pack_linear_tc(Wn), ops.pack_linear_tc(w(self.B_3).contiguous())
         else:
             Wn_t = Wn.t().contiguous()                               # k-major [H_in][5H or 4H]
@@ -120,6 +135,7 @@ class _GatedGCNBase(nn.Module):
         dev = h.device
         pk = self._pack(dev)
         ws = ws if ws is not None else {}
+        backend = 'ffma' if effective_backend(H) == 'ffma' else 'tc'
         n_blocks = 5 if self._symmetric else 4
         P = ws.get('P')
         if P is None or P.shape != (gi.N, n_blocks * H):
@@ -128,14 +144,14 @@ class _GatedGCNBase(nn.Module):
         if Fb is None or Fb.shape != (gi.N, H):
             Fb = ws['F'] = torch.empty((gi.N, H), dtype=torch.float32, device=dev)
         carry = ws.get('carry')
-        n_chunks = gi.num_chunks(H, _BACKEND)
+        n_chunks = gi.num_chunks(H, backend)
         if carry is None or carry.shape != (n_chunks, 4, H):
             carry = ws['carry'] = torch.empty((n_chunks, 4, H), dtype=torch.float32, device=dev)
         h_out = ws.pop('h_spare', None)
         if h_out is None or h_out.shape != h.shape or h_out.data_ptr() == h.data_ptr():
             h_out = torch.empty_like(h)
         flags = self._flags()
-        if _BACKEND == 'tc':
+        if backend == 'tc':
             ops.node_linear_tc(h, pk['Wn_t'], pk['bn'], n_blocks * H, out=P)
             tile_flags, epoch = gi.tile_flags(H) if H > 128 else (None, 0)
             ops.edge_forward_tc(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry,
@@ -144,9 +160,46 @@ class _GatedGCNBase(nn.Module):
             ops.node_linear(h, pk['Wn_t'], pk['bn'], out=P)
             ops.edge_forward(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry, flags)
         ops.node_update(gi, H, P, e_pos, Fb, carry, h, pk['scale_h'], pk['shift_h'], h_out, flags,
-                        gi.chunk(H, _BACKEND))
+                        gi.chunk(H, backend))
         ws['h_spare'] = h  # ping-pong: the caller no longer needs the input h
         return h_out, e_pos
+
+    def forward_positions16(self, gi: GraphIndex, h32, h16, e16, ws=None):
+        """One layer on the split16 path: ``h32`` fp32 rows (residual), ``h16`` / ``e16`` split fp16 images
+        (the tensor-core operands).  ``e16`` is updated IN PLACE; returns ``(h32', h16', e16)``."""
+        if self.training:
+            raise NotImplementedError('training mode runs through gnnome_b200.autograd (not built yet)')
+        if self.in_channels != self.out_channels:
+            raise NotImplementedError('in_channels != out_channels is not supported by the CUDA path')
+        H = self.out_channels
+        dev = h32.device
+        pk = self._pack(dev)
+        ws = ws if ws is not None else {}
+        n_blocks = 5 if self._symmetric else 4
+
+        def buf(name, shape, dtype=torch.float32):
+            t = ws.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = ws[name] = torch.empty(shape, dtype=dtype, device=dev)
+            return t
+
+        P = buf('P', (gi.N, n_blocks * H))
+        Fb = buf('F', (gi.N, H))
+        carry = buf('carry', (gi.num_chunks(H, 'tc'), 4, H))
+        h_out = ws.pop('h_spare', None)
+        if h_out is None or h_out.shape != h32.shape or h_out.data_ptr() == h32.data_ptr():
+            h_out = torch.empty_like(h32)
+        h16_out = ws.pop('h16_spare', None)
+        if h16_out is None or h16_out.shape != h16.shape or h16_out.data_ptr() == h16.data_ptr():
+            h16_out = torch.empty_like(h16)
+        flags = self._flags()
+        ops.node_linear_tc2(h16, pk['Wn_t'], pk['bn'], n_blocks * H, out=P)
+        tile_flags, epoch = gi.tile_flags(H) if H > 128 else (None, 0)
+        ops.edge_forward_tc2(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e16, Fb, carry, tile_flags, epoch, flags)
+        ops.node_update2(gi, H, P, e16, Fb, carry, h32, pk['scale_h'], pk['shift_h'], h_out, h16_out, flags,
+                         gi.chunk(H, 'tc'))
+        ws['h_spare'], ws['h16_spare'] = h32, h16   # ping-pong: the caller no longer needs the inputs
+        return h_out, h16_out, e16
 
     # -- reference-compatible layer API ------------------------------------------------------------
     def forward(self, g, h, e):
@@ -155,9 +208,14 @@ class _GatedGCNBase(nn.Module):
         out_dev = h.device
         h_d = h.detach().to(device=gi.device, dtype=torch.float32).contiguous()
         e_d = e.detach().to(device=gi.device, dtype=torch.float32).contiguous()
-        e_pos = ops.gather_rows(e_d, gi.in_eid[:gi.E])
-        h_new, e_pos = self.forward_positions(gi, h_d.clone(), e_pos)
-        e_new = ops.scatter_rows(e_pos, gi.in_eid[:gi.E])
+        if state_format(self.out_channels) == 'split16' and gi.E > 0:
+            e16 = ops.split_rows(e_d, gi.in_eid[:gi.E])
+            h_new, _, e16 = self.forward_positions16(gi, h_d.clone(), ops.split_rows(h_d), e16)
+            e_new = ops.merge_rows(e16, gi.in_eid[:gi.E])
+        else:
+            e_pos = ops.gather_rows(e_d, gi.in_eid[:gi.E])
+            h_new, e_pos = self.forward_positions(gi, h_d.clone(), e_pos)
+            e_new = ops.scatter_rows(e_pos, gi.in_eid[:gi.E])
         h_new = F.dropout(h_new, self.dropout, training=self.training)  # :139
         return h_new.to(out_dev), e_new.to(out_dev)
 

@@ -5,7 +5,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..graph import GraphIndex
-from .gated_gcn import GatedGCN, SymGatedGCN
+from .gated_gcn import GatedGCN, SymGatedGCN, state_format
 
 
 class _Processor(nn.Module):
@@ -23,11 +23,21 @@ class _Processor(nn.Module):
             h, e_pos = conv.forward_positions(gi, h, e_pos, ws)
         return h, e_pos
 
+    def forward_positions16(self, gi, h32, h16, e16):
+        ws = {}
+        for conv in self.convs:
+            h32, h16, e16 = conv.forward_positions16(gi, h32, h16, e16, ws)
+        return h32, h16, e16
+
     def forward(self, graph, h, e):
         gi = GraphIndex.from_graph(graph)
         out_dev = h.device
         h_d = h.detach().to(device=gi.device, dtype=torch.float32).contiguous().clone()
         e_d = e.detach().to(device=gi.device, dtype=torch.float32).contiguous()
+        if state_format(h_d.shape[1]) == 'split16' and gi.E > 0:
+            e16 = ops.split_rows(e_d, gi.in_eid[:gi.E])
+            h_d, _, e16 = self.forward_positions16(gi, h_d, ops.split_rows(h_d), e16)
+            return h_d.to(out_dev), ops.merge_rows(e16, gi.in_eid[:gi.E]).to(out_dev)
         e_pos = ops.gather_rows(e_d, gi.in_eid[:gi.E])
         h_d, e_pos = self.forward_positions(gi, h_d, e_pos)
         return h_d.to(out_dev), ops.scatter_rows(e_pos, gi.in_eid[:gi.E]).to(out_dev)

@@ -35,6 +35,35 @@ class ScorePredictor(nn.Module):
                           self.W3.bias.detach().to(**dev), e_pos, scores)
         return scores
 
+    def _node_weights(self, dev):
+        H, hs = self.in_features, self.hidden_edge_scores
+        W1 = self.W1.weight.detach().to(**dev)
+        Wn = torch.cat((W1[:, :H], W1[:, H:2 * H]), dim=0).contiguous()          # [2hs][H] (nn.Linear layout)
+        bias = torch.cat((torch.zeros(hs, **dev), self.W1.bias.detach().to(**dev)))
+        return Wn, bias
+
+    def node_rows16(self, x16):
+        """``node_rows`` from the split16 images of x, on the tensor cores."""
+        dev = dict(device=x16.device, dtype=torch.float32)
+        Wn, bias = self._node_weights(dev)
+        return ops.node_linear_tc2(x16, ops.pack_linear_tc(Wn), bias, Wn.shape[0])
+
+    def score_positions16(self, gi: GraphIndex, S, e16, scores=None, tensor_cores=True):
+        """``score_positions`` with the edge state given as split16 images; ``tensor_cores=False`` runs the
+        CUDA-core cross-check kernel."""
+        H, hs = self.in_features, self.hidden_edge_scores
+        dev = dict(device=e16.device, dtype=torch.float32)
+        W1e = self.W1.weight.detach().to(**dev)[:, 2 * H:].contiguous()         # [hs][H]
+        if scores is None:
+            scores = torch.empty((gi.E, 1), **dev)
+        tail = (self.W2.weight.detach().to(**dev).contiguous(), self.W2.bias.detach().to(**dev),
+                self.W3.weight.detach().to(**dev).reshape(-1).contiguous(), self.W3.bias.detach().to(**dev), e16, scores)
+        if tensor_cores:
+            ops.score_forward_tc2(gi, H, hs, S, ops.pack_linear_tc(W1e), *tail)
+        else:
+            ops.score_forward2(gi, H, hs, S, W1e.t().contiguous(), *tail)
+        return scores
+
     def forward_positions(self, gi: GraphIndex, x, e_pos):
         """Scores in ORIGINAL edge-id order, shape (E, 1), from position-ordered edge rows."""
         return self.score_positions(gi, self.node_rows(x), e_pos)

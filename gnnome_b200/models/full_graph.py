@@ -11,7 +11,8 @@ import torch.nn as nn
 
 from .. import layers
 from ..graph import GraphIndex
-from ..layers.encoders import encode_rows
+from ..layers.encoders import encode_rows, encode_rows2
+from ..layers.gated_gcn import state_format
 
 
 def _to_dev(t, device):
@@ -34,6 +35,11 @@ class SymGatedGCNModel(nn.Module):
         gi = GraphIndex.from_graph(graph)
         out_dev = x.device
         x_d, e_d = _to_dev(x, gi.device), _to_dev(e, gi.device)
+        if state_format(self.linear2_node.out_features) == 'split16' and gi.E > 0:
+            h16, h32 = encode_rows2(x_d, None, self.linear1_node, self.linear2_node, gi.N, want32=True)   # :26
+            e16, _ = encode_rows2(e_d, gi.in_eid, self.linear1_edge, self.linear2_edge, gi.E)              # :27
+            h32, h16, e16 = self.gnn.forward_positions16(gi, h32, h16, e16)                              # :28
+            return self.predictor.score_positions16(gi, self.predictor.node_rows16(h16), e16).to(out_dev)  # :29
         h = encode_rows(x_d, None, self.linear1_node, self.linear2_node, gi.N)             # :26
         e_pos = encode_rows(e_d, gi.in_eid, self.linear1_edge, self.linear2_edge, gi.E)    # :27
         h, e_pos = self.gnn.forward_positions(gi, h, e_pos)                               # :28
@@ -54,6 +60,12 @@ class GatedGCNModel(nn.Module):
         gi = GraphIndex.from_graph(graph)
         out_dev = x.device
         x_d, e_d = _to_dev(x, gi.device), _to_dev(e, gi.device)
+        if self.directed and state_format(self.node_encoder.linear2.out_features) == 'split16' and gi.E > 0:
+            ne, ee = self.node_encoder, self.edge_encoder
+            h16, h32 = encode_rows2(x_d, None, ne.linear1, ne.linear2, gi.N, want32=True)
+            e16, _ = encode_rows2(e_d, gi.in_eid, ee.linear1, ee.linear2, gi.E)
+            h32, h16, e16 = self.gnn.forward_positions16(gi, h32, h16, e16)
+            return self.predictor.score_positions16(gi, self.predictor.node_rows16(h16), e16).to(out_dev)
         h = encode_rows(x_d, None, self.node_encoder.linear1, self.node_encoder.linear2, gi.N)
         if self.directed:                                                                  # :45-46
             e_pos = encode_rows(e_d, gi.in_eid, self.edge_encoder.linear1, self.edge_encoder.linear2, gi.E)

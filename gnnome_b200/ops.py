@@ -186,3 +186,118 @@ def scatter_rows(x, idx, out=None):
         _lib.check(lib.gnb_scatter_rows(_f32(x, 'x'), idx.data_ptr(), rows, W, _f32(out, 'out'),
                                         current_stream_ptr(x.device)), 'gnb_scatter_rows')
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# split16 path (TMA-fed tcgen05 kernels): state = fp16 images [2][rows][K] (hi, lo), x = 16 * (hi + lo)
+# ------------------------------------------------------------------------------------------------
+def _img(t, name):
+    if t.dtype != torch.float16 or not t.is_cuda or not t.is_contiguous() or t.ndim != 3 or t.shape[0] != 2:
+        raise ValueError(f'{name} must be a contiguous float16 CUDA tensor of shape [2][rows][K] (got {t.dtype}, '
+                         f'{tuple(t.shape)}, {t.device})')
+    return t.data_ptr()
+
+
+def empty_split16(rows, K, device):
+    return torch.empty((2, rows, K), dtype=torch.float16, device=device)
+
+
+def split_rows(x, idx=None, out=None):
+    """fp32 rows -> split16 images; ``out[r] = split(x[idx[r]])`` when ``idx`` is given."""
+    lib = _lib.load()
+    rows = x.shape[0] if idx is None else idx.numel()
+    K = x.shape[1]
+    if out is None:
+        out = empty_split16(rows, K, x.device)
+    with _logged('gnb_split_rows', x.device):
+        _lib.check(lib.gnb_split_rows(_f32(x, 'x'), _opt(idx), rows, K, _img(out, 'out'), current_stream_ptr(x.device)),
+                   'gnb_split_rows')
+    return out
+
+
+def merge_rows(x16, idx=None, out=None):
+    """split16 images -> fp32 rows; ``out[idx[r]] = merge(x16[r])`` when ``idx`` is given."""
+    lib = _lib.load()
+    _, rows, K = x16.shape
+    if out is None:
+        out = torch.empty((rows, K), dtype=torch.float32, device=x16.device)
+    with _logged('gnb_merge_rows', x16.device):
+        _lib.check(lib.gnb_merge_rows(_img(x16, 'x16'), _opt(idx), rows, K, _f32(out, 'out'),
+                                      current_stream_ptr(x16.device)), 'gnb_merge_rows')
+    return out
+
+
+def encode2(x, idx, W1, b1, W2t, b2, rows, want16=True, want32=False):
+    """Two-layer encoder writing split16 images and / or fp32 rows: returns ``(out16, out32)``."""
+    lib = _lib.load()
+    hid, in_f = W1.shape
+    H = W2t.shape[1]
+    out16 = empty_split16(rows, H, x.device) if want16 else None
+    out32 = torch.empty((rows, H), dtype=torch.float32, device=x.device) if want32 else None
+    with _logged('gnb_encode2', x.device):
+        _lib.check(lib.gnb_encode2(_f32(x, 'x'), _opt(idx), rows, in_f, hid, H, _f32(W1, 'W1'), _f32(b1, 'b1'),
+                                   _f32(W2t, 'W2t'), _f32(b2, 'b2'), _opt(out16), _opt(out32),
+                                   current_stream_ptr(x.device)), 'gnb_encode2')
+    return out16, out32
+
+
+def node_linear_tc2(x16, Wp, bias, M, out=None):
+    """out = X @ W.T + bias with X in split16 format; Wp = pack_linear_tc(W[M][K])."""
+    lib = _lib.load()
+    _, rows, K = x16.shape
+    if out is None:
+        out = torch.empty((rows, M), dtype=torch.float32, device=x16.device)
+    with _logged('gnb_node_linear_tc2', x16.device):
+        _lib.check(lib.gnb_node_linear_tc2(_img(x16, 'x16'), rows, K, Wp.data_ptr(), _f32(bias, 'bias'), M,
+                                           _f32(out, 'out'), out.stride(0), current_stream_ptr(x16.device)),
+                   'gnb_node_linear_tc2')
+    return out
+
+
+def edge_forward_tc2(gi: GraphIndex, H, P, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags):
+    lib = _lib.load()
+    with _logged('gnb_edge_forward_tc2', e16.device):
+        _lib.check(lib.gnb_edge_forward_tc2(gi.ref(), H, _f32(P, 'P'), P.stride(0), Wp.data_ptr(),
+                                            _f32(scale_e, 'scale_e'), _f32(shift_e, 'shift_e'), _img(e16, 'e16'),
+                                            _f32(F, 'F'), _f32(carry, 'carry'), _opt(tile_flags), epoch, flags,
+                                            current_stream_ptr(e16.device)), 'gnb_edge_forward_tc2')
+
+
+def node_update2(gi: GraphIndex, H, P, e16, F, carry, h_in, scale_h, shift_h, h_out, h16_out, flags, chunk,
+                 node_begin=0, node_end=None, xp_ptr=None, xp_row=None, xp_buf=None):
+    lib = _lib.load()
+    node_end = gi.N if node_end is None else node_end
+    with _logged('gnb_node_update2', h_in.device):
+        _lib.check(lib.gnb_node_update2(gi.ref(), H, _f32(P, 'P'), P.stride(0), _img(e16, 'e16'), _f32(F, 'F'),
+                                        _f32(carry, 'carry'), _f32(h_in, 'h_in'), _f32(scale_h, 'scale_h'),
+                                        _f32(shift_h, 'shift_h'), _f32(h_out, 'h_out'),
+                                        None if h16_out is None else _img(h16_out, 'h16_out'), flags, chunk,
+                                        node_begin, node_end, _opt(xp_ptr), _opt(xp_row),
+                                        None if xp_buf is None else _f32(xp_buf, 'xp_buf'),
+                                        current_stream_ptr(h_in.device)), 'gnb_node_update2')
+
+
+def reverse_partial2(gi: GraphIndex, H, P, e16, node_begin, node_end, out):
+    lib = _lib.load()
+    with _logged('gnb_reverse_partial2', e16.device):
+        _lib.check(lib.gnb_reverse_partial2(gi.ref(), H, _f32(P, 'P'), P.stride(0), _img(e16, 'e16'), node_begin,
+                                            node_end, _f32(out, 'out'), current_stream_ptr(e16.device)),
+                   'gnb_reverse_partial2')
+
+
+def score_forward2(gi: GraphIndex, H, hs, S, W1e_t, W2, b2, W3, b3, e16, scores):
+    lib = _lib.load()
+    with _logged('gnb_score_forward2', e16.device):
+        _lib.check(lib.gnb_score_forward2(gi.ref(), H, hs, _f32(S, 'S'), _f32(W1e_t, 'W1e_t'), _f32(W2, 'W2'),
+                                          _f32(b2, 'b2'), _f32(W3, 'W3'), _f32(b3, 'b3'), _img(e16, 'e16'),
+                                          _f32(scores, 'scores'), current_stream_ptr(e16.device)),
+                   'gnb_score_forward2')
+
+
+def score_forward_tc2(gi: GraphIndex, H, hs, S, Wp, W2, b2, W3, b3, e16, scores):
+    lib = _lib.load()
+    with _logged('gnb_score_forward_tc2', e16.device):
+        _lib.check(lib.gnb_score_forward_tc2(gi.ref(), H, hs, _f32(S, 'S'), Wp.data_ptr(), _f32(W2, 'W2'),
+                                             _f32(b2, 'b2'), _f32(W3, 'W3'), _f32(b3, 'b3'), _img(e16, 'e16'),
+                                             _f32(scores, 'scores'), current_stream_ptr(e16.device)),
+                   'gnb_score_forward_tc2')

@@ -123,12 +123,16 @@ class HaloPlan:
 # the per-op contracts the sharded forward is written against
 # ------------------------------------------------------------------------------------------------
 class CudaKernels:
-    """The product path: every method is one C-ABI call (gnnome_b200.ops)."""
+    """The product path: every method is one C-ABI call (gnnome_b200.ops).  Node / edge state objects are
+    opaque to ShardedForward: on the split16 path h = (fp32 rows, fp16 images), e = fp16 images; on the
+    fp32 path both are plain fp32 matrices."""
 
     def __init__(self, device):
         from . import ops
         from .graph import GraphIndex
-        self.ops, self.GraphIndex, self.device = ops, GraphIndex, device
+        from .layers.gated_gcn import state_format
+        self.ops, self.GraphIndex, self.device, self.state_format = ops, GraphIndex, device, state_format
+        self.spare = {}
 
     def stage(self, src_local, dst_local, n_local):
         return self.GraphIndex(src_local, dst_local, n_local, self.device)
@@ -136,14 +140,31 @@ class CudaKernels:
     def position_eids(self, gi):
         return gi.in_eid[:gi.E]
 
-    def encode(self, x, idx, lin1, lin2, rows):
-        from .layers.encoders import encode_rows
-        return encode_rows(x, idx, lin1, lin2, rows)
+    def _split(self, H):
+        return self.state_format(H) == 'split16'
+
+    def encode_nodes(self, x, lin1, lin2, rows):
+        from .layers.encoders import encode_rows, encode_rows2
+        if self._split(lin2.out_features):
+            h16, h32 = encode_rows2(x, None, lin1, lin2, rows, want32=True)
+            return (h32, h16)
+        return encode_rows(x, None, lin1, lin2, rows)
+
+    def encode_edges(self, e, idx, lin1, lin2, rows):
+        from .layers.encoders import encode_rows, encode_rows2
+        if self._split(lin2.out_features):
+            return encode_rows2(e, idx, lin1, lin2, rows)[0]
+        return encode_rows(e, idx, lin1, lin2, rows)
+
+    def width(self, h):
+        return (h[0] if isinstance(h, tuple) else h).shape[1]
 
     def layer_pack(self, conv):
         return conv._pack(self.device)
 
     def node_linear_layer(self, pk, h, M, out):
+        if isinstance(h, tuple):
+            return self.ops.node_linear_tc2(h[1], pk['Wn_t'], pk['bn'], M, out=out)
         return self.ops.node_linear_tc(h, pk['Wn_t'], pk['bn'], M, out=out)
 
     def gather_rows(self, table, idx, out=None):
@@ -151,23 +172,44 @@ class CudaKernels:
 
     def edge_forward(self, gi, H, P, pk, e_pos, F, carry, flags):
         tile_flags, epoch = gi.tile_flags(H) if H > 128 else (None, 0)
-        self.ops.edge_forward_tc(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, F, carry,
-                                 tile_flags, epoch, flags)
+        fn = self.ops.edge_forward_tc2 if e_pos.dtype == torch.float16 else self.ops.edge_forward_tc
+        fn(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, F, carry, tile_flags, epoch, flags)
 
     def carry_shape(self, gi, H):
         return (gi.num_chunks(H, 'tc'), 4, H)
 
     def reverse_partial(self, gi, H, P, e_pos, node_begin, node_end, out):
-        self.ops.reverse_partial(gi, H, P, e_pos, node_begin, node_end, out)
+        fn = self.ops.reverse_partial2 if e_pos.dtype == torch.float16 else self.ops.reverse_partial
+        fn(gi, H, P, e_pos, node_begin, node_end, out)
 
-    def node_update(self, gi, H, P, pk, e_pos, F, carry, h_in, h_out, flags, n_own, xp_ptr, xp_row, xp_buf):
-        self.ops.node_update(gi, H, P, e_pos, F, carry, h_in, pk['scale_h'], pk['shift_h'], h_out, flags,
-                             gi.chunk(H, 'tc'), node_end=n_own, xp_ptr=xp_ptr, xp_row=xp_row, xp_buf=xp_buf)
+    def _like(self, name, t):
+        b = self.spare.pop(name, None)
+        if b is None or b.shape != t.shape or b.dtype != t.dtype or b.data_ptr() == t.data_ptr():
+            b = torch.empty_like(t)
+        return b
 
-    def score_node_rows(self, predictor, x):
-        return predictor.node_rows(x)
+    def node_update(self, gi, H, P, pk, e_pos, F, carry, h_in, flags, n_own, xp_ptr, xp_row, xp_buf):
+        """Returns the new node state; the input state's buffers are recycled for the next layer."""
+        kw = dict(node_end=n_own, xp_ptr=xp_ptr, xp_row=xp_row, xp_buf=xp_buf)
+        if isinstance(h_in, tuple):
+            h32, h16 = h_in
+            o32, o16 = self._like('h32', h32), self._like('h16', h16)
+            self.ops.node_update2(gi, H, P, e_pos, F, carry, h32, pk['scale_h'], pk['shift_h'], o32, o16, flags,
+                                  gi.chunk(H, 'tc'), **kw)
+            self.spare['h32'], self.spare['h16'] = h32, h16
+            return (o32, o16)
+        out = self._like('h32', h_in)
+        self.ops.node_update(gi, H, P, e_pos, F, carry, h_in, pk['scale_h'], pk['shift_h'], out, flags,
+                             gi.chunk(H, 'tc'), **kw)
+        self.spare['h32'] = h_in
+        return out
+
+    def score_node_rows(self, predictor, h):
+        return predictor.node_rows16(h[1]) if isinstance(h, tuple) else predictor.node_rows(h)
 
     def score_forward(self, predictor, gi, S, e_pos, scores):
+        if e_pos.dtype == torch.float16:
+            return predictor.score_positions16(gi, S, e_pos, scores)
         return predictor.score_positions(gi, S, e_pos, scores)
 
 
@@ -219,13 +261,12 @@ class ShardedForward:
         else:
             lin_n = (m.node_encoder.linear1, m.node_encoder.linear2)
             lin_e = (m.edge_encoder.linear1, m.edge_encoder.linear2)
-        h = k.encode(x_own, None, lin_n[0], lin_n[1], n_own)
-        e_pos = k.encode(e_own, k.position_eids(gi), lin_e[0], lin_e[1], sh.num_edges)
-        H = h.shape[1]
+        h = k.encode_nodes(x_own, lin_n[0], lin_n[1], n_own)
+        e_pos = k.encode_edges(e_own, k.position_eids(gi), lin_e[0], lin_e[1], sh.num_edges)
+        H = k.width(h)
         nb = 5 if self.sym else 4
         P = self._buf('P', (n_local, nb * H))
         Fb = self._buf('F', (n_local, H))
-        h_out = self._buf('h2', (n_own, H))
         for conv in m.gnn.convs:
             pk = k.layer_pack(conv)
             flags = conv._flags()
@@ -241,11 +282,9 @@ class ShardedForward:
                 part = self._buf('s2', (n_halo, 2 * H))
                 k.reverse_partial(gi, H, P, e_pos, n_own, n_local, part)
                 xp_buf = plan.to_owners(part, self._buf('r2', (plan.n_send, 2 * H)))
-            k.node_update(gi, H, P, pk, e_pos, Fb, carry, h, h_out, flags, n_own,
-                          plan.xp_ptr if xp_buf is not None else None,
-                          plan.xp_row if xp_buf is not None else None, xp_buf)
-            h, h_out = h_out, h
-        self.ws['h2'] = h_out
+            h = k.node_update(gi, H, P, pk, e_pos, Fb, carry, h, flags, n_own,
+                              plan.xp_ptr if xp_buf is not None else None,
+                              plan.xp_row if xp_buf is not None else None, xp_buf)
         # ---- predictor: S = [x W1s^T | x W1d^T + b1]; the src half of remote sources is a halo ----
         S_own = k.score_node_rows(m.predictor, h)
         hs = S_own.shape[1] // 2

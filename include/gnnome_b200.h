@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 3
+#define GNB_ABI_VERSION 4
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -169,6 +169,62 @@ int gnb_gather_rows_ld(const float* in, int64_t ld_in, const int32_t* idx, int64
 /* out[idx[r]][0:W] = in[r][0:W] */
 int gnb_scatter_rows(const float* in, const int32_t* idx, int64_t rows, int W, float* out,
                      void* stream);
+
+/* ---- split16 path: TMA-fed tcgen05 kernels (the product path for H in {64, 128, 256}) ------------------
+ * Edge and node state is held in HBM as TWO row-major fp16 images per matrix X[rows][K],
+ *   hi[r][k] = fp16(x / 16),  lo[r][k] = fp16(x / 16 - hi[r][k])     (x ~ 16 * (hi + lo), 22 significant bits),
+ * hi at the base pointer, lo at base + rows * K halves: 4 bytes per element like fp32, but the images are the
+ * tensor-core operands, so tiles go HBM -> shared memory -> MMA through the TMA engine with no conversion
+ * instructions, and the updated state goes back with TMA stores. */
+
+/* Bytes of the split16 images of a [rows][K] matrix. */
+size_t gnb_split16_bytes(int64_t rows, int K);
+
+/* out16[r] = split(in[idx ? idx[r] : r])   (fp32 rows -> images; idx = gnb_graph_t.in_eid moves edge rows from
+ * edge-id order to dst-sorted position order).  K % 8 == 0. */
+int gnb_split_rows(const float* in, const int32_t* idx, int64_t rows, int K, void* out16, void* stream);
+/* out[idx ? idx[r] : r] = merge(in16[r])   (images -> fp32 rows). */
+int gnb_merge_rows(const void* in16, const int32_t* idx, int64_t rows, int K, float* out, void* stream);
+
+/* gnb_encode with split16 and / or fp32 output (either may be NULL): models/full_graph.py:26-27.
+ * in_f <= 4, hid <= 64. */
+int gnb_encode2(const float* in, const int32_t* idx, int64_t rows, int in_f, int hid, int H,
+                const float* W1, const float* b1, const float* W2t, const float* b2, void* out16,
+                float* out32, void* stream);
+
+/* gnb_node_linear_tc with X given as split16 images (gated_gcn_full.py:91-96, score_predictor.py:13-14). */
+int gnb_node_linear_tc2(const void* X16, int64_t rows, int K, const void* Wp, const float* bias, int M,
+                        float* out, int64_t ld_out, void* stream);
+
+/* gnb_edge_forward_tc with the edge state e16 in split16 format, updated in place (gated_gcn_full.py:97,104-114).
+ * Same P / carry / tile_flags / epoch contract; carry granularity gnb_edge_chunk_tc(H). */
+int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
+                         const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
+                         int32_t* tile_flags, int epoch, int flags, void* stream);
+
+/* gnb_node_update with e' read from split16 images; writes h' as fp32 rows (h_out, row i) and, if h16_out is
+ * not NULL, as split16 images of the rows node_begin .. node_end (row i - node_begin) for the next layer's
+ * gnb_node_linear_tc2 (gated_gcn_full.py:117-137). */
+int gnb_node_update2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* e16,
+                     const float* F, const float* carry, const float* h_in, const float* scale_h,
+                     const float* shift_h, float* h_out, void* h16_out, int flags, int chunk,
+                     int64_t node_begin, int64_t node_end, const int32_t* xp_ptr, const int32_t* xp_row,
+                     const float* xp_buf, void* stream);
+/* gnb_reverse_partial with e' read from split16 images. */
+int gnb_reverse_partial2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* e16,
+                         int64_t node_begin, int64_t node_end, float* out, void* stream);
+
+/* ScorePredictor on the tensor cores (score_predictor.py:12-24): the e * W1e^T product runs on tcgen05 with the
+ * e tile brought in by TMA; Wp = gnb_pack_linear_tc(W1e [hs][H]) (zero-padded to 128 rows).  Other arguments
+ * as gnb_score_forward. */
+int gnb_score_forward_tc2(const gnb_graph_t* g, int H, int hs, const float* S, const void* Wp,
+                          const float* W2, const float* b2, const float* W3, const float* b3,
+                          const void* e16, float* scores, void* stream);
+
+/* gnb_score_forward (CUDA cores) with the edge state given as split16 images: cross-check of the above. */
+int gnb_score_forward2(const gnb_graph_t* g, int H, int hs, const float* S, const float* W1e_t,
+                       const float* W2, const float* b2, const float* W3, const float* b3,
+                       const void* e16, float* scores, void* stream);
 
 #ifdef __cplusplus
 }

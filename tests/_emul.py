@@ -26,6 +26,15 @@ class EmulKernels:
     def position_eids(self, gi):
         return gi.in_eid
 
+    def encode_nodes(self, x, lin1, lin2, rows):
+        return self.encode(x, None, lin1, lin2, rows)
+
+    def encode_edges(self, e, idx, lin1, lin2, rows):
+        return self.encode(e, idx, lin1, lin2, rows)
+
+    def width(self, h):
+        return h.shape[1]
+
     def encode(self, x, idx, lin1, lin2, rows):
         x = x.to(self.dtype)
         if idx is not None:
@@ -88,7 +97,7 @@ class EmulKernels:
         out[:, :H] = num[node_begin:node_end]
         out[:, H:] = den[node_begin:node_end]
 
-    def node_update(self, gi, H, P, conv, e_pos, Fb, carry, h_in, h_out, flags, n_own, xp_ptr, xp_row, xp_buf):
+    def node_update(self, gi, H, P, conv, e_pos, Fb, carry, h_in, flags, n_own, xp_ptr, xp_row, xp_buf):
         sym = bool(flags & 1)
         u = P[:n_own, (4 if sym else 3) * H:(5 if sym else 4) * H] + Fb[:n_own]
         if sym:
@@ -104,7 +113,7 @@ class EmulKernels:
         v = torch.relu(u * sc + sh)
         if flags & 2:
             v = v + h_in[:n_own]
-        h_out.copy_(v)
+        return v
 
     def score_node_rows(self, pred, x):
         H, hs = pred.in_features, pred.hidden_edge_scores

@@ -21,12 +21,13 @@ def gnb():
     return gnnome_b200
 
 
-@pytest.fixture(params=['tc', 'ffma'])
+@pytest.fixture(params=['tc2', 'tc', 'ffma'])
 def backend(request, gnb):
-    """'tc' = tcgen05 tensor-core kernels (the product path), 'ffma' = CUDA-core fp32 kernels."""
+    """'tc2' = TMA-fed tcgen05 kernels on split fp16 state (the product path), 'tc' = first-generation tcgen05
+    kernels on fp32 state, 'ffma' = CUDA-core fp32 kernels."""
     gnb.set_backend(request.param)
     yield request.param
-    gnb.set_backend('tc')
+    gnb.set_backend('tc2')
 
 
 def _graph(n, m, seed):
@@ -83,6 +84,48 @@ def test_node_linear(gnb, rows, K, M):
     assert (out_tc.cpu().double() - ref).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize('rows,K,M', [(1, 64, 128), (130, 64, 320), (1000, 128, 640), (777, 256, 1280), (64, 256, 128)])
+def test_node_linear_tc2(gnb, rows, K, M):
+    """TMA-fed edition: X given as split fp16 (hi, lo) images."""
+    from gnnome_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    a, w, b = torch.randn(rows, K, generator=g), torch.randn(M, K, generator=g) / K ** 0.5, torch.randn(M, generator=g)
+    out = ops.node_linear_tc2(ops.split_rows(a.cuda()), ops.pack_linear_tc(w.cuda()), b.cuda(), M)
+    ref = (a.double() @ w.double().t() + b.double())
+    assert (out.cpu().double() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize('rows,K', [(1, 64), (77, 128), (1000, 256)])
+def test_split16_roundtrip(gnb, rows, K):
+    """x -> (hi, lo) fp16 images -> x keeps 22 significant bits (absolute floor 2^-20 from fp16 subnormals)."""
+    from gnnome_b200 import ops
+    x = torch.randn(rows, K, device='cuda') * 5
+    idx = torch.randperm(rows, device='cuda').to(torch.int32)
+    y = ops.merge_rows(ops.split_rows(x))
+    assert ((y - x).abs() <= x.abs() * 2.0 ** -22 + 2.0 ** -20).all()
+    y2 = ops.merge_rows(ops.split_rows(x, idx), idx)       # gather on the way in, scatter on the way out
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize('H,hs', [(64, 64), (128, 32), (256, 64), (256, 128)])
+def test_score_tc2_vs_cuda_core(gnb, H, hs):
+    from gnnome_b200 import ops
+    src, dst, n, _, _ = _graph(3000, 18002, seed=hs)
+    gi = gnb.GraphIndex(src, dst, n)
+    torch.manual_seed(H + hs)
+    pred = gnb.layers.ScorePredictor(H, hs)
+    x, e = torch.randn(n, H, device='cuda'), torch.randn(gi.E, H, device='cuda')
+    with torch.no_grad():
+        S = pred.node_rows16(ops.split_rows(x))
+        e16 = ops.split_rows(e)
+        a = pred.score_positions16(gi, S, e16, tensor_cores=True)
+        b = pred.score_positions16(gi, S, e16, tensor_cores=False)
+        p = {'predictor.' + k: v.double() for k, v in pred.state_dict().items()}
+        ref = R.score_predictor(p, 'predictor.', src.long(), dst.long(), x.cpu().double(), e.cpu().double()[torch.argsort(gi.in_eid[:gi.E].cpu().long())])
+    assert (a - b).abs().max().item() < 2e-5
+    assert (a.cpu().double() - ref).abs().max().item() < 5e-5
+
+
 @pytest.mark.parametrize('scale', [1e-3, 1.0, 300.0, 3e4])
 def test_node_linear_tc_dynamic_range(gnb, scale):
     """The fp16 split keeps fp32-level accuracy up to |x| ~ 1e5; below |x| ~ 1 the fp16 subnormal
@@ -107,6 +150,11 @@ def test_encode(gnb, rows, H):
     ref = torch.relu(x[idx.long()].double() @ W1.double().t() + b1.double()) @ W2.double().t() + b2.double()
     out = ops.encode(x.cuda(), idx.cuda(), W1.cuda(), b1.cuda(), W2.t().contiguous().cuda(), b2.cuda(), rows)
     assert (out.cpu().double() - ref).abs().max().item() < 1e-5
+    if H >= 64:
+        o16, o32 = ops.encode2(x.cuda(), idx.cuda(), W1.cuda(), b1.cuda(), W2.t().contiguous().cuda(), b2.cuda(), rows,
+                               want16=True, want32=True)
+        assert (o32.cpu().double() - ref).abs().max().item() < 1e-5
+        assert (ops.merge_rows(o16).cpu().double() - ref).abs().max().item() < 2e-5
     out2 = ops.encode(x[:rows].contiguous().cuda(), None, W1.cuda(), b1.cuda(), W2.t().contiguous().cuda(), b2.cuda(), rows)
     ref2 = torch.relu(x[:rows].double() @ W1.double().t() + b1.double()) @ W2.double().t() + b2.double()
     assert (out2.cpu().double() - ref2).abs().max().item() < 1e-5
