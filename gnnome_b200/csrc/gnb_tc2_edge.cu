@@ -213,6 +213,16 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
     //   (c / 64) * KB_BYTES + row * 128 + ((((c % 64) / 8) ^ (row % 8)) * 16) + (c % 8) * 2
     const uint32_t col_base = (uint32_t)((c >> 6) * T::KB_BYTES + sub * kE2Chunk * 128 + ((c & 7) << 1));
     const uint32_t col_x = (uint32_t)((c & 63) >> 3);
+    // Hand a finished stage to the store warp.  A warp must not arrive for its group's tile j before phase j-1 of
+    // sfull has completed (a warp with little to do -- the empty half of a ragged last tile -- could otherwise
+    // complete the previous phase on behalf of a slower warp that is still writing its rows).
+    int jj = 0;   // tiles of this group handled so far
+    auto stage_done = [&]() {
+      if (jj > 0) mbar_wait(&sfull[grp], (jj - 1) & 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull[grp]);
+      ++jj;
+    };
     int i = 0;
     for (int64_t t = worker; t < my_tiles; t += workers, ++i) {
       if (i % kE2Groups != grp) continue;
@@ -226,10 +236,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&dempty[grp]);
-          mbar_arrive(&sfull[grp]);
-        }
+        if (lane == 0) mbar_arrive(&dempty[grp]);
+        stage_done();
         continue;
       }
       const int* ia = idx_area + s * kE2IdxInts;
@@ -338,8 +346,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
       }
       // e' is in the stage: make it visible to the async proxy, then hand the stage to the store warp
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[grp]);
+      stage_done();
     }
   }
   tc_fence_before();

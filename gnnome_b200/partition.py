@@ -234,13 +234,16 @@ class ShardedForward:
         if not self.sym and not getattr(model, 'directed', True):
             raise NotImplementedError('GatedGCNModel(directed=False) is not sharded')
         src, dst = torch.as_tensor(src), torch.as_tensor(dst)
+        if torch.device(device).type == 'cuda':          # build the index tables on the GPU (sort / unique of E ids)
+            src, dst = src.to(device), dst.to(device)
         self.shard = sh = Shard(src, dst, num_nodes, rank, world)
         self.plan = HaloPlan(sh, device, group)
         self.owned_edge_ids = sh.edge_ids
         self.gi = self.k.stage(sh.src_local.to(device), sh.dst_local.to(device), sh.n_local)
         self.x_own = torch.as_tensor(x)[sh.lo:sh.hi].to(device=device, dtype=dtype).contiguous()
-        self.e_own = torch.as_tensor(e)[sh.edge_ids.to(torch.as_tensor(e).device)].to(
-            device=device, dtype=dtype).contiguous()
+        e = torch.as_tensor(e)
+        self.e_own = e[sh.edge_ids.to(e.device)].to(device=device, dtype=dtype).contiguous()
+        del src, dst
         self._host = None
         self.ws = {}
 
