@@ -416,7 +416,7 @@ struct ScoreCfg {
       ((size_t)R * H + 16 * HS + (size_t)R * HS + (size_t)R * TS + 32 * TS + 32 + 32) * 4 + (size_t)3 * R * 4;
 };
 
-// kSplit16: e points at the split16 images of the edge state (fp16 hi [E][H], then lo [E][H]; x = 16 * (hi + lo))
+// kSplit16: e points at the split16 edge state (fp16 rows [hi 0..H | lo 0..H]; x = 16 * (hi + lo))
 template <int H, int HS, bool kSplit16>
 __global__ void __launch_bounds__(kThreads)
 score_forward_kernel(gnb_graph_t g, const float* __restrict__ S, const float* __restrict__ W1e_t,
@@ -454,10 +454,9 @@ score_forward_kernel(gnb_graph_t g, const float* __restrict__ S, const float* __
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p0 + row < E) {
         if (kSplit16) {
-          const __half* e_hi = reinterpret_cast<const __half*>(e);
-          const __half* e_lo = e_hi + E * H;
-          const uint2 hh = *reinterpret_cast<const uint2*>(e_hi + (p0 + row) * H + q4 * 4);
-          const uint2 ll = *reinterpret_cast<const uint2*>(e_lo + (p0 + row) * H + q4 * 4);
+          const __half* e16 = reinterpret_cast<const __half*>(e);
+          const uint2 hh = *reinterpret_cast<const uint2*>(e16 + (p0 + row) * 2 * H + q4 * 4);
+          const uint2 ll = *reinterpret_cast<const uint2*>(e16 + (p0 + row) * 2 * H + H + q4 * 4);
           const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hh.x));
           const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&hh.y));
           const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ll.x));

@@ -22,18 +22,18 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-int make_image_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows) {
+int make_state_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return GNB_E_ARCH;
   }
   if (((uintptr_t)base & 15) != 0 || K % kKB != 0 || rows <= 0 || box_rows <= 0 || box_rows > 256) {
-    set_error("make_image_map: bad image (base %p rows %lld K %d box %d)", base, (long long)rows, K, box_rows);
+    set_error("make_state_map: bad matrix (base %p rows %lld K %d box %d)", base, (long long)rows, K, box_rows);
     return GNB_E_INVALID;
   }
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(__half)};
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)2 * K * sizeof(__half)};
   const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -51,8 +51,6 @@ __global__ void split_rows_kernel(const float* __restrict__ in, const int32_t* _
                                   __half* __restrict__ out) {
   const int k8 = K / 8;
   const int64_t total = rows * k8;
-  __half* hi = out;
-  __half* lo = out + rows * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / k8;
     const int c = (int)(i - r * k8) * 8;
@@ -63,8 +61,8 @@ __global__ void split_rows_kernel(const float* __restrict__ in, const int32_t* _
                   b.x * kXScale, b.y * kXScale, b.z * kXScale, b.w * kXScale};
     uint4 h, l;
     split8(x, h, l);
-    *reinterpret_cast<uint4*>(hi + r * K + c) = h;
-    *reinterpret_cast<uint4*>(lo + r * K + c) = l;
+    *reinterpret_cast<uint4*>(out + r * 2 * K + c) = h;
+    *reinterpret_cast<uint4*>(out + r * 2 * K + K + c) = l;
   }
 }
 
@@ -73,14 +71,12 @@ __global__ void merge_rows_kernel(const __half* __restrict__ in, const int32_t* 
                                   float* __restrict__ out) {
   const int k8 = K / 8;
   const int64_t total = rows * k8;
-  const __half* hi = in;
-  const __half* lo = in + rows * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / k8;
     const int c = (int)(i - r * k8) * 8;
     const int64_t rd = idx ? (int64_t)idx[r] : r;
-    const uint4 h = *reinterpret_cast<const uint4*>(hi + r * K + c);
-    const uint4 l = *reinterpret_cast<const uint4*>(lo + r * K + c);
+    const uint4 h = *reinterpret_cast<const uint4*>(in + r * 2 * K + c);
+    const uint4 l = *reinterpret_cast<const uint4*>(in + r * 2 * K + K + c);
     const __half2* hp = reinterpret_cast<const __half2*>(&h);
     const __half2* lp = reinterpret_cast<const __half2*>(&l);
     float o[8];

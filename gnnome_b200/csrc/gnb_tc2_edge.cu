@@ -64,13 +64,12 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
-template <int H>
+template <int H, bool kTiming>
 __global__ void __launch_bounds__(kE2Threads, 1)
-edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                        gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ Wp,
+edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ Wp,
                         const float* __restrict__ scale_e, const float* __restrict__ shift_e,
                         float* __restrict__ F, float* __restrict__ carry, int32_t* tile_flags, int epoch, int flags,
-                        int workers) {
+                        int workers, unsigned long long* timing) {
   using C = Edge2Cfg<H>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -100,8 +99,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
       mbar_init(&sfull[i], C::LIVE_WARPS);
     }
     fence_barrier_init();
-    prefetch_tensormap(&map_hi);
-    prefetch_tensormap(&map_lo);
+    prefetch_tensormap(&map_e);
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
@@ -126,19 +124,37 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
       if (lane == 0 && t > 0) r[4] = g.in_dst[t * kE2NT - 1];
       if (lane == 1 && (t + 1) * kE2NT < E) r[4] = g.in_dst[(t + 1) * kE2NT];
     };
+    // Every node row is touched for the first time by SOME gather of the epilogue, and that one would wait for
+    // HBM; the producer knows the tile's endpoints two to three tile periods before the epilogue needs them, so
+    // it pulls this CTA's slices of the (B1h, A2h)[src] and B2h[dst] rows into L2 ahead of time.
+    auto prefetch_rows = [&](const int (&r)[5]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int sj = r[k], dj = r[2 + k];
+        if (dj >= 0) {
+          const char* a = reinterpret_cast<const char*>(P + (int64_t)sj * ldP + 2 * half * C::HC);
+#pragma unroll
+          for (int l = 0; l < C::HC * 8 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
+          const char* b = reinterpret_cast<const char*>(P + (int64_t)dj * ldP + 2 * H + half * C::HC);
+#pragma unroll
+          for (int l = 0; l < C::HC * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + l * 128));
+        }
+      }
+    };
     int cur[5], nxt[5];
     if (worker < num_tiles) load_idx(worker, cur);
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
-      mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1);
+      prefetch_rows(cur);
+      mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
       if (lane == 0) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
         for (int kb = 0; kb < T::KBLOCKS; ++kb) {
-          tma_load_2d(stage + kb * T::KB_BYTES, &map_hi, kb * kKB, (int)(t * kE2NT), &full[s]);
-          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_lo, kb * kKB, (int)(t * kE2NT), &full[s]);
+          tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s]);
+          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s]);
         }
       }
       if (t + workers < num_tiles) load_idx(t + workers, nxt);   // in flight while this tile's indices are published
@@ -157,11 +173,11 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB, d = i % kE2Groups;
-      mbar_wait(&full[s], (i / C::NB) & 1);
+      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
       // both channel halves read whole rows of e and overwrite their own half in place: tell the other half
       // that this CTA's copy of tile t has left global memory
       if (C::NH > 1 && lane == 0) red_release_add2(tile_flags + t, 1);
-      mbar_wait(&dempty[d], ((i / kE2Groups) & 1) ^ 1);
+      mbar_wait_sleep(&dempty[d], ((i / kE2Groups) & 1) ^ 1, 32);
       tc_fence_after();
       if (lane == 0) {
         issue_tile_mma_sw128<H, kE2NT>(tmem_base, tmem_base + C::D_COL0 + d * kE2NT,
@@ -178,7 +194,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
       for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
         if (i % kE2Groups != grp) continue;
         const int s = i % C::NB;
-        mbar_wait(&sfull[grp], j & 1);
+        mbar_wait_sleep(&sfull[grp], j & 1);
         ++j;
         if (C::NH > 1) {  // the other half must have read tile t before our channels of it are overwritten
           while (ld_acquire2(tile_flags + t) < C::NH * epoch) __nanosleep(32);
@@ -187,8 +203,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
 #pragma unroll
         for (int kbl = 0; kbl < C::HC / kKB; ++kbl) {
           const int kb = half * (C::HC / kKB) + kbl;
-          tma_store_2d(&map_hi, stage + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
-          tma_store_2d(&map_lo, stage + T::IMG_BYTES + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
+          tma_store_2d(&map_e, stage + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
+          tma_store_2d(&map_e, stage + T::IMG_BYTES + kb * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT));
         }
         tma_store_commit();
         tma_store_wait_read();
@@ -206,8 +222,9 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
     const int64_t my_tiles = ch_ok ? num_tiles : 0;   // warps without live channels (H = 64) sit the loop out
     const float sc = scale_e[c], sh = shift_e[c];
     const bool residual = flags & GNB_F_RESIDUAL;
-    const float* Pc = P + 2 * c;             // (B1h[c], A2h[c]) interleaved
-    const float* Pb2 = P + 2 * H + c;        // B2h[c]
+    const char* Pc = reinterpret_cast<const char*>(P + 2 * c);        // (B1h[c], A2h[c]) interleaved
+    const char* Pb2 = reinterpret_cast<const char*>(P + 2 * H + c);   // B2h[c]
+    const int ldPb = (int)(ldP * (int64_t)sizeof(float));            // row pitch in bytes (< 2^31, checked by the host)
     constexpr unsigned kFull = 0xffffffffu;
     // this thread's column of the stage: element (row, c) of an image sits at
     //   (c / 64) * KB_BYTES + row * 128 + ((((c % 64) / 8) ^ (row % 8)) * 16) + (c % 8) * 2
@@ -216,6 +233,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
     // Hand a finished stage to the store warp.  A warp must not arrive for its group's tile j before phase j-1 of
     // sfull has completed (a warp with little to do -- the empty half of a ragged last tile -- could otherwise
     // complete the previous phase on behalf of a slower warp that is still writing its rows).
+    // optional cycle accounting (gnb_debug_edge_timing): [full wait, dfull wait, batches, flush + hand-off, tiles]
+    unsigned long long tm[5] = {0, 0, 0, 0, 0};
     int jj = 0;   // tiles of this group handled so far
     auto stage_done = [&]() {
       if (jj > 0) mbar_wait(&sfull[grp], (jj - 1) & 1);
@@ -230,9 +249,11 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
       const int64_t cs = t * kE2NT + sub * kE2Chunk;
       const bool live = cs < E;              // warp-uniform; false only for the second half of a ragged last tile
       const int n = live ? (int)((E - cs < kE2Chunk) ? (E - cs) : kE2Chunk) : 0;
-      mbar_wait(&full[s], (i / C::NB) & 1);  // indices published (and the operand tile has landed)
+      const long long t0 = kTiming ? clock64() : 0;
+      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);  // indices published (and the operand tile has landed)
+      const long long t1 = kTiming ? clock64() : 0;
       if (!live) {  // nothing to compute, but the barriers still have to be fed
-        mbar_wait(&dfull[grp], (i / kE2Groups) & 1);
+        mbar_wait_sleep(&dfull[grp], (i / kE2Groups) & 1);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
@@ -258,82 +279,110 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
       const uint32_t st_hi = smem_u32(bufs + (size_t)s * T::BUF_BYTES) + col_base;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + grp * kE2NT + sub * kE2Chunk;
       int cur = -1;
-      float num = 0.f, den = 0.f, b2s = 0.f;
+      float num = 0.f, den = 0.f;
 
-      // Software pipeline over four batches of eight edges: the gathers of batch b+1 are in flight while batch b
-      // is computed.  fa = (B1h, A2h)[src], fb = B2h[dst] (fetched only where a destination segment opens).
+      // Software pipeline over four batches of eight edges: the gathers of batch b+1 -- fa = (B1h, A2h)[src] and
+      // fb = B2h[dst], one coalesced row segment per warp each -- are in flight while batch b is computed.
+      // A batch is computed in two passes: (1) branch-free, eight edges interleaved: z -> e' -> split fp16 -> stage,
+      // sigma; (2) the per-destination bookkeeping, a straight sum when no segment opens inside the batch.
       constexpr int kEB = 8;
-      float2 ba[2][kEB];
-      float b2v[2][kEB];
-      auto fetch = [&](int b, float2 (&fa)[kEB], float (&fb)[kEB]) {
-        const unsigned mb = segmask >> (b * kEB);
+      const int my_dst_c = my_dst < 0 ? 0 : my_dst;   // rows past the end of a ragged tile: any valid address
+      auto fetch = [&](int b, float2 (&xa)[kEB], float (&xb)[kEB]) {
 #pragma unroll
         for (int u = 0; u < kEB; ++u) {
           const int sj = __shfl_sync(kFull, my_src, b * kEB + u);
-          fa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj * ldP));
-          fb[u] = 0.f;
-          if (mb & (1u << u)) {   // warp-uniform
-            const int dj = __shfl_sync(kFull, my_dst, b * kEB + u);
-            fb[u] = __ldg(Pb2 + (int64_t)dj * ldP);
-          }
+          const int dj = __shfl_sync(kFull, my_dst_c, b * kEB + u);
+          xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj * ldPb));
+          xb[u] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj * ldPb));
         }
       };
-      auto compute = [&](int b, const float2 (&fa)[kEB], const float (&fb)[kEB]) {
-        uint32_t zr[kEB];
-        tmem_ld8(taddr + b * kEB, zr);
-        tmem_ld_wait();
-        if (b == kE2Chunk / kEB - 1) {   // last read of this accumulator buffer: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&dempty[grp]);
-        }
-        const unsigned mb = segmask >> (b * kEB);
+      auto compute = [&](int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
+        // Two half-batches of four edges.  The shared-memory accesses are volatile asm statements, which the
+        // compiler keeps in program order: the loads of a half-batch come first and its stores last, so that the
+        // four per-edge dependency chains in between interleave.
 #pragma unroll
-        for (int u = 0; u < kEB; ++u) {
-          if (mb & (1u << u)) {          // warp-uniform: close the running segment, open the next
-            if (cur >= 0) {
-              if (cur == head_dst) {
-                carry[(chunk * 4 + 0) * H + c] = num;
-                carry[(chunk * 4 + 1) * H + c] = den;
-              } else {
-                F[(int64_t)cur * H + c] = gate_div(num, den);
-              }
+        for (int hb = 0; hb < kEB; hb += 4) {
+          uint32_t zr[4];
+          tmem_ld4(taddr + b * kEB + hb, zr);
+          float ein[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            ein[w] = 0.f;
+            if (residual) {   // row (b*8 + hb + w) of the chunk: row % 8 == hb + w
+              const uint32_t a = st_hi + (uint32_t)((b * kEB + hb + w) * 128) + ((col_x ^ (uint32_t)(hb + w)) << 4);
+              const __half_raw hr{lds_u16(a)}, lr{lds_u16(a + T::IMG_BYTES)};
+              ein[w] = (__half2float(__half(hr)) + __half2float(__half(lr))) * kWScale;
             }
-            cur = __shfl_sync(kFull, my_dst, b * kEB + u);
-            num = 0.f;
-            den = 0.f;
-            b2s = fmaf(fb[u], sc, sh);
           }
-          // row b*8+u of the chunk: row % 8 == u
-          const uint32_t a_hi = st_hi + (uint32_t)((b * kEB + u) * 128) + ((col_x ^ (uint32_t)u) << 4);
-          const uint32_t a_lo = a_hi + T::IMG_BYTES;
-          float v = fmaf(__uint_as_float(zr[u]) + fa[u].x, sc, b2s);
-          v = fmaxf(v, 0.f);
-          if (residual) {
-            const __half_raw hr{lds_u16(a_hi)}, lr{lds_u16(a_lo)};
-            v += (__half2float(__half(hr)) + __half2float(__half(lr))) * kWScale;
+          tmem_ld_wait();
+          if (b == kE2Chunk / kEB - 1 && hb == 4) {   // last read of this accumulator buffer: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dempty[grp]);
           }
-          if (b * kEB + u < n) {
+          float sg[4];
+          uint32_t pk[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int u = hb + w;
+            const float v = fmaxf(fmaf(__uint_as_float(zr[w]) + xa[u].x + xb[u], sc, sh), 0.f) + ein[w];
             __half nh, nl;
             split1(v, nh, nl);
-            sts_u16(a_hi, __half_raw(nh).x);
-            sts_u16(a_lo, __half_raw(nl).x);
-            const float sg = sigmoidf_fast(v);
-            num = fmaf(sg, fa[u].y, num);
-            den += sg;
+            pk[w] = (uint32_t)__half_raw(nh).x | ((uint32_t)__half_raw(nl).x << 16);
+            sg[w] = (b * kEB + u < n) ? sigmoidf_fast(v) : 0.f;
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            if (b * kEB + hb + w < n) {
+              const uint32_t a = st_hi + (uint32_t)((b * kEB + hb + w) * 128) + ((col_x ^ (uint32_t)(hb + w)) << 4);
+              sts_u16(a, (uint16_t)(pk[w] & 0xffffu));
+              sts_u16(a + T::IMG_BYTES, (uint16_t)(pk[w] >> 16));
+            }
+          }
+          const unsigned mb = (segmask >> (b * kEB + hb)) & 0xfu;
+          if (mb == 0) {                 // warp-uniform: the four edges continue the running segment
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              num = fmaf(sg[w], xa[hb + w].y, num);
+              den += sg[w];
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              if (mb & (1u << w)) {      // warp-uniform: close the running segment, open the next
+                if (cur >= 0) {
+                  if (cur == head_dst) {
+                    carry[(chunk * 4 + 0) * H + c] = num;
+                    carry[(chunk * 4 + 1) * H + c] = den;
+                  } else {
+                    F[(int64_t)cur * H + c] = gate_div(num, den);
+                  }
+                }
+                cur = __shfl_sync(kFull, my_dst, b * kEB + hb + w);
+                num = 0.f;
+                den = 0.f;
+              }
+              num = fmaf(sg[w], xa[hb + w].y, num);
+              den += sg[w];
+            }
           }
         }
       };
-      fetch(0, ba[0], b2v[0]);
-      mbar_wait(&dfull[grp], (i / kE2Groups) & 1);
+      float2 fa0[kEB], fa1[kEB];
+      float fb0[kEB], fb1[kEB];
+      fetch(0, fa0, fb0);
+      const long long t2 = kTiming ? clock64() : 0;
+      mbar_wait_sleep(&dfull[grp], (i / kE2Groups) & 1, 32);
       tc_fence_after();
+      const long long t3 = kTiming ? clock64() : 0;
 #pragma unroll 1
       for (int b = 0; b < kE2Chunk / kEB; b += 2) {
-        fetch(b + 1, ba[1], b2v[1]);
-        compute(b, ba[0], b2v[0]);
-        if (b + 2 < kE2Chunk / kEB) fetch(b + 2, ba[0], b2v[0]);
-        compute(b + 1, ba[1], b2v[1]);
+        fetch(b + 1, fa1, fb1);
+        compute(b, fa0, fb0);
+        if (b + 2 < kE2Chunk / kEB) fetch(b + 2, fa0, fb0);
+        compute(b + 1, fa1, fb1);
       }
+      const long long t4 = kTiming ? clock64() : 0;
       // close the segment that is still open at the end of the chunk
       if (cur == tail_dst) {
         carry[(chunk * 4 + 2) * H + c] = num;
@@ -347,6 +396,14 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
       // e' is in the stage: make it visible to the async proxy, then hand the stage to the store warp
       fence_proxy_async();
       stage_done();
+      if (kTiming) {
+        const long long t5 = clock64();
+        tm[0] += t1 - t0; tm[1] += t3 - t2; tm[2] += (t4 - t3) + (t2 - t1); tm[3] += t5 - t4; tm[4] += 1;
+      }
+    }
+    if (kTiming && timing != nullptr && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) timing[((size_t)blockIdx.x * 32 + warp) * 5 + k] = tm[k];
     }
   }
   tc_fence_before();
@@ -354,30 +411,31 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// debugging aid: when set, every epilogue warp leaves its cycle accounting in timing[blockIdx][warp][5]
+static unsigned long long* g_edge_timing = nullptr;
+
 template <int H>
 static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t ldP, const void* Wp,
                                  const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
                                  int32_t* tile_flags, int epoch, int flags, cudaStream_t stream) {
   using C = Edge2Cfg<H>;
-  cudaError_t err = cudaFuncSetAttribute(edge_forward_tc2_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::SMEM);
+  auto kern = g_edge_timing ? edge_forward_tc2_kernel<H, true> : edge_forward_tc2_kernel<H, false>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (err != cudaSuccess) {
     set_error("gnb_edge_forward_tc2: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(err));
     return (int)err;
   }
   if (C::NH > 1) GNB_REQUIRE(tile_flags != nullptr && epoch > 0, "gnb_edge_forward_tc2: H=%d needs tile_flags and epoch >= 1", H);
   const int64_t E = g->num_edges;
-  CUtensorMap map_hi, map_lo;
-  int rc = make_image_map(&map_hi, e16, E, H, kE2NT);
-  if (rc) return rc;
-  rc = make_image_map(&map_lo, (const __half*)e16 + E * H, E, H, kE2NT);
+  CUtensorMap map_e;
+  int rc = make_state_map(&map_e, e16, E, H, kE2NT);
   if (rc) return rc;
   const int64_t num_tiles = (E + kE2NT - 1) / kE2NT;
   int workers = sm_count() / C::NH;
   if (workers > num_tiles) workers = (int)num_tiles;
   // every CTA must be resident at the same time (the channel halves wait on each other's flags)
-  edge_forward_tc2_kernel<H><<<workers * C::NH, kE2Threads, C::SMEM, stream>>>(
-      map_hi, map_lo, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, tile_flags, epoch, flags, workers);
+  kern<<<workers * C::NH, kE2Threads, C::SMEM, stream>>>(
+      map_e, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, tile_flags, epoch, flags, workers, g_edge_timing);
   return check_launch("gnb_edge_forward_tc2");
 }
 
@@ -386,6 +444,8 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
 
 using namespace gnb;
 
+extern "C" void gnb_debug_edge_timing(void* buf) { tc::g_edge_timing = (unsigned long long*)buf; }
+
 extern "C" int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
                                     const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
                                     int32_t* tile_flags, int epoch, int flags, void* stream) {
@@ -393,8 +453,8 @@ extern "C" int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P,
   if (g->num_edges == 0) return 0;
   GNB_REQUIRE(g->in_src && g->in_dst, "graph not staged");
   GNB_REQUIRE(P && Wp && scale_e && shift_e && e16 && F && carry, "null pointer");
-  GNB_REQUIRE(ldP >= ((flags & GNB_F_SYMMETRIC) ? 5 : 4) * (int64_t)H && ldP % 2 == 0, "ldP=%lld too small",
-              (long long)ldP);
+  GNB_REQUIRE(ldP >= ((flags & GNB_F_SYMMETRIC) ? 5 : 4) * (int64_t)H && ldP % 2 == 0 && ldP < ((int64_t)1 << 29),
+              "ldP=%lld out of range", (long long)ldP);
   GNB_REQUIRE(((uintptr_t)P % 8 == 0) && ((uintptr_t)e16 % 16 == 0) && ((uintptr_t)Wp % 16 == 0),
               "gnb_edge_forward_tc2: e16 must be 16-byte aligned, P 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;

@@ -30,8 +30,7 @@ struct Lin2Cfg {
 
 template <int K>
 __global__ void __launch_bounds__(kLin2Threads, 1)
-node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                       int64_t rows, const __half* __restrict__ Wp, const float* __restrict__ bias, int M,
+node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, const __half* __restrict__ Wp, const float* __restrict__ bias, int M,
                        float* __restrict__ out, int64_t ld_out, int nblk, int workers) {
   using C = Lin2Cfg<K>;
   using T = typename C::T;
@@ -58,8 +57,7 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       mbar_init(&dempty[i], 4);
     }
     fence_barrier_init();
-    prefetch_tensormap(&map_hi);
-    prefetch_tensormap(&map_lo);
+    prefetch_tensormap(&map_x);
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
@@ -83,8 +81,8 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
         for (int kb = 0; kb < T::KBLOCKS; ++kb) {
-          tma_load_2d(stage + kb * T::KB_BYTES, &map_hi, kb * kKB, (int)(t * kLin2NT), &full[s]);
-          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_lo, kb * kKB, (int)(t * kLin2NT), &full[s]);
+          tma_load_2d(stage + kb * T::KB_BYTES, &map_x, kb * kKB, (int)(t * kLin2NT), &full[s]);
+          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_x, K + kb * kKB, (int)(t * kLin2NT), &full[s]);
         }
       }
     }
@@ -158,10 +156,8 @@ static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, c
     set_error("gnb_node_linear_tc2: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(e));
     return (int)e;
   }
-  CUtensorMap map_hi, map_lo;
-  int rc = make_image_map(&map_hi, X16, rows, K, kLin2NT);
-  if (rc) return rc;
-  rc = make_image_map(&map_lo, (const __half*)X16 + rows * K, rows, K, kLin2NT);
+  CUtensorMap map_x;
+  int rc = make_state_map(&map_x, X16, rows, K, kLin2NT);
   if (rc) return rc;
   const int nblk = (M + kM - 1) / kM;
   const int sms = sm_count();
@@ -169,7 +165,7 @@ static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, c
   const int64_t num_tiles = (rows + kLin2NT - 1) / kLin2NT;
   int workers = sms / nblk;
   if (workers > num_tiles) workers = (int)num_tiles;
-  node_linear_tc2_kernel<K><<<workers * nblk, kLin2Threads, C::SMEM, stream>>>(map_hi, map_lo, rows, (const __half*)Wp,
+  node_linear_tc2_kernel<K><<<workers * nblk, kLin2Threads, C::SMEM, stream>>>(map_x, rows, (const __half*)Wp,
                                                                               bias, M, out, ld_out, nblk, workers);
   return check_launch("gnb_node_linear_tc2");
 }

@@ -34,8 +34,6 @@ encode2_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx, in
   float bias[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) bias[k] = b2[c0 + k];
-  __half* hi = out16;
-  __half* lo = out16 ? out16 + rows * H : nullptr;
   const int64_t num_it = (rows + RPB - 1) / RPB;
   for (int64_t it = blockIdx.x; it < num_it; it += gridDim.x) {
     const int64_t r0 = it * RPB + (int64_t)rg * kEncR;
@@ -86,8 +84,8 @@ encode2_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx, in
         for (int k = 0; k < 8; ++k) xs[k] = acc[r][k] * kXScale;
         uint4 h, l;
         split8(xs, h, l);
-        *reinterpret_cast<uint4*>(hi + row * H + c0) = h;
-        *reinterpret_cast<uint4*>(lo + row * H + c0) = l;
+        *reinterpret_cast<uint4*>(out16 + row * 2 * H + c0) = h;
+        *reinterpret_cast<uint4*>(out16 + row * 2 * H + H + c0) = l;
       }
     }
   }
@@ -137,10 +135,16 @@ __device__ __forceinline__ F8 f8_merge(const uint4& h, const uint4& l) {
 }
 
 constexpr int kNu2Threads = 256;
-constexpr int kNu2Batch = 2;   // out-edges in flight per thread
+constexpr int kNu2Batch = 4;   // out-edges in flight per thread (64 bytes each)
 
+// H / 8 threads ("group") per node, 8 channels per thread: per out-edge a 16-byte hi + 16-byte lo load of the e'
+// row (one contiguous 4H-byte row per group) and a 32-byte load of A3h[dst].  Latency is what bounds this kernel
+// (CSR pointers -> edge indices -> rows are dependent loads), so: the pointers of the group's NEXT node are
+// fetched one iteration ahead, everything that depends only on the node id is issued before the edge loop, the
+// group loads the indices of up to H / 8 edges with one instruction and broadcasts them by shuffle, and four
+// edge rows are in flight per thread.
 template <int H>
-__global__ void __launch_bounds__(kNu2Threads, 3)
+__global__ void __launch_bounds__(kNu2Threads, 2)
 node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ e16,
                     const float* __restrict__ F, const float* __restrict__ carry, const float* __restrict__ h_in,
                     const float* __restrict__ scale_h, const float* __restrict__ shift_h, float* __restrict__ h_out,
@@ -152,40 +156,63 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
   const int t = threadIdx.x % TPN, slot = threadIdx.x / TPN;
   const int c0 = t * 8;
   const bool sym = flags & GNB_F_SYMMETRIC, residual = flags & GNB_F_RESIDUAL;
+  const bool agg = sym || partial_out;
   const int a1_off = sym ? 4 * H : 3 * H;
-  const __half* e_hi = e16;
-  const __half* e_lo = e16 + g.num_edges * H;
-  const int64_t n_upd = node_end - node_begin;
-  __half* h_hi = h16_out;
-  __half* h_lo = h16_out ? h16_out + n_upd * H : nullptr;
-  for (int64_t i = node_begin + (int64_t)blockIdx.x * NPB + slot; i < node_end; i += (int64_t)gridDim.x * NPB) {
+  const unsigned gmask = TPN >= 32 ? 0xffffffffu : (((1u << TPN) - 1u) << (((threadIdx.x & 31) / TPN) * TPN));
+  const int64_t stride = (int64_t)gridDim.x * NPB;
+  int64_t i = node_begin + (int64_t)blockIdx.x * NPB + slot;
+  int qa = 0, qb = 0, pa = 0, pb = 0;
+  if (i < node_end) {
+    if (agg) { qa = g.out_ptr[i]; qb = g.out_ptr[i + 1]; }
+    if (!partial_out) { pa = g.in_ptr[i]; pb = g.in_ptr[i + 1]; }
+  }
+  for (; i < node_end; i += stride) {
+    int nqa = 0, nqb = 0, npa = 0, npb = 0;   // CSR pointers of this group's next node: one iteration ahead
+    if (i + stride < node_end) {
+      if (agg) { nqa = g.out_ptr[i + stride]; nqb = g.out_ptr[i + stride + 1]; }
+      if (!partial_out) { npa = g.in_ptr[i + stride]; npb = g.in_ptr[i + stride + 1]; }
+    }
+    // ---- everything that depends on the node id only ------------------------------------------------
+    F8 a1 = f8_zero(), hin = f8_zero(), f = f8_zero();
+    const bool f_direct = pb > pa && pa / chunk == (pb - 1) / chunk;   // the whole in-segment sits in one chunk
+    if (!partial_out) {
+      a1 = f8_ldg(P + i * ldP + a1_off + c0);
+      if (residual) hin = f8_load(h_in + i * H + c0);
+      if (f_direct) f = f8_load(F + i * H + c0);
+    }
     // ---- Bk: gate-normalised sum over out-edges ------------------------------------------------
     F8 bk = f8_zero();
-    if (sym || partial_out) {
+    if (agg) {
       F8 num = f8_zero(), den = f8_zero();
-      const int qa = g.out_ptr[i], qb = g.out_ptr[i + 1];
-      for (int q0 = qa; q0 < qb; q0 += kNu2Batch) {
-        uint4 eh[kNu2Batch], el[kNu2Batch];
-        F8 av[kNu2Batch];
+      for (int q0 = qa; q0 < qb; q0 += TPN) {
+        const int cnt = (qb - q0 < TPN) ? (qb - q0) : TPN;   // group-uniform
+        int myp = 0, myd = 0;
+        if (t < cnt) {
+          myp = g.out_pos[q0 + t];
+          myd = g.out_dst[q0 + t];
+        }
+        for (int u0 = 0; u0 < cnt; u0 += kNu2Batch) {
+          uint4 eh[kNu2Batch], el[kNu2Batch];
+          F8 av[kNu2Batch];
 #pragma unroll
-        for (int u = 0; u < kNu2Batch; ++u) {
-          if (q0 + u < qb) {
-            const int64_t p = g.out_pos[q0 + u];
-            const int64_t d = g.out_dst[q0 + u];
-            eh[u] = *reinterpret_cast<const uint4*>(e_hi + p * H + c0);
-            el[u] = *reinterpret_cast<const uint4*>(e_lo + p * H + c0);
+          for (int u = 0; u < kNu2Batch; ++u) {
+            const int lane_u = (u0 + u < cnt) ? (u0 + u) : (cnt - 1);   // tail slots repeat the last edge (loads only)
+            const int64_t p = __shfl_sync(gmask, myp, lane_u, TPN);
+            const int64_t d = __shfl_sync(gmask, myd, lane_u, TPN);
+            eh[u] = *reinterpret_cast<const uint4*>(e16 + p * 2 * H + c0);
+            el[u] = *reinterpret_cast<const uint4*>(e16 + p * 2 * H + H + c0);
             av[u] = f8_ldg(P + d * ldP + 3 * H + c0);
           }
-        }
 #pragma unroll
-        for (int u = 0; u < kNu2Batch; ++u) {
-          if (q0 + u < qb) {
-            const F8 ev = f8_merge(eh[u], el[u]);
+          for (int u = 0; u < kNu2Batch; ++u) {
+            if (u0 + u < cnt) {
+              const F8 ev = f8_merge(eh[u], el[u]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float sg = sigmoidf_fast(ev.v[k]);
-              num.v[k] = fmaf(sg, av[u].v[k], num.v[k]);
-              den.v[k] += sg;
+              for (int k = 0; k < 8; ++k) {
+                const float sg = sigmoidf_fast(ev.v[k]);
+                num.v[k] = fmaf(sg, av[u].v[k], num.v[k]);
+                den.v[k] += sg;
+              }
             }
           }
         }
@@ -193,6 +220,7 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       if (partial_out) {  // multi-GPU: un-normalised partial sums of a halo source node, for its owner
         f8_store(partial_out + (i - node_begin) * 2 * H + c0, num);
         f8_store(partial_out + (i - node_begin) * 2 * H + H + c0, den);
+        qa = nqa; qb = nqb;
         continue;
       }
       if (xp_ptr) {       // multi-GPU: partial sums other ranks computed for this node, in rank order
@@ -210,38 +238,26 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       for (int k = 0; k < 8; ++k) bk.v[k] = gate_div(num.v[k], den.v[k]);
     }
     // ---- F: from the edge pass, resolving chunk-straddling segments ---------------------------------
-    F8 f = f8_zero();
-    const int pa = g.in_ptr[i], pb = g.in_ptr[i + 1];
-    if (pb > pa) {
+    if (pb > pa && !f_direct) {
       const int k0 = pa / chunk, k1 = (pb - 1) / chunk;
-      if (k0 == k1) {
-        f = f8_load(F + i * H + c0);
-      } else {
-        F8 num = f8_zero(), den = f8_zero();
-        for (int k = k0; k < k1; ++k) {
-          const F8 a = f8_load(carry + ((int64_t)k * 4 + 2) * H + c0), b = f8_load(carry + ((int64_t)k * 4 + 3) * H + c0);
+      F8 num = f8_zero(), den = f8_zero();
+      for (int k = k0; k < k1; ++k) {
+        const F8 a = f8_load(carry + ((int64_t)k * 4 + 2) * H + c0), b = f8_load(carry + ((int64_t)k * 4 + 3) * H + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            num.v[j] += a.v[j];
-            den.v[j] += b.v[j];
-          }
+        for (int jx = 0; jx < 8; ++jx) {
+          num.v[jx] += a.v[jx];
+          den.v[jx] += b.v[jx];
         }
-        const F8 a = f8_load(carry + ((int64_t)k1 * 4 + 0) * H + c0), b = f8_load(carry + ((int64_t)k1 * 4 + 1) * H + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f.v[j] = gate_div(num.v[j] + a.v[j], den.v[j] + b.v[j]);
       }
+      const F8 a = f8_load(carry + ((int64_t)k1 * 4 + 0) * H + c0), b = f8_load(carry + ((int64_t)k1 * 4 + 1) * H + c0);
+#pragma unroll
+      for (int jx = 0; jx < 8; ++jx) f.v[jx] = gate_div(num.v[jx] + a.v[jx], den.v[jx] + b.v[jx]);
     }
     // ---- h' = relu(bn_h(A1h + F + Bk)) + h ---------------------------------------------------------
-    const F8 a1 = f8_ldg(P + i * ldP + a1_off + c0);
     const F8 sc = f8_ldg(scale_h + c0), sh = f8_ldg(shift_h + c0);   // L1-resident; not worth 16 live registers
     F8 u;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) u.v[k] = fmaxf(fmaf(a1.v[k] + f.v[k] + bk.v[k], sc.v[k], sh.v[k]), 0.f);
-    if (residual) {
-      const F8 hin = f8_load(h_in + i * H + c0);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) u.v[k] += hin.v[k];
-    }
+    for (int k = 0; k < 8; ++k) u.v[k] = fmaxf(fmaf(a1.v[k] + f.v[k] + bk.v[k], sc.v[k], sh.v[k]), 0.f) + hin.v[k];
     f8_store(h_out + i * H + c0, u);
     if (h16_out) {
       float xs[8];
@@ -249,9 +265,10 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       for (int k = 0; k < 8; ++k) xs[k] = u.v[k] * kXScale;
       uint4 hh, ll;
       split8(xs, hh, ll);
-      *reinterpret_cast<uint4*>(h_hi + (i - node_begin) * H + c0) = hh;
-      *reinterpret_cast<uint4*>(h_lo + (i - node_begin) * H + c0) = ll;
+      *reinterpret_cast<uint4*>(h16_out + (i - node_begin) * 2 * H + c0) = hh;
+      *reinterpret_cast<uint4*>(h16_out + (i - node_begin) * 2 * H + H + c0) = ll;
     }
+    qa = nqa; qb = nqb; pa = npa; pb = npb;
   }
 }
 
@@ -281,7 +298,7 @@ static int node_update2_impl(const gnb_graph_t* g, const float* P, int64_t ldP, 
                              cudaStream_t stream) {
   constexpr int NPB = kNu2Threads / (H / 8);
   const int64_t items = (node_end - node_begin + NPB - 1) / NPB;
-  const int64_t cap = (int64_t)sm_count() * 32;
+  const int64_t cap = (int64_t)sm_count() * 2;   // persistent: two resident CTAs per SM, grid-stride over the nodes
   node_update2_kernel<H><<<(unsigned)(items < cap ? items : cap), kNu2Threads, 0, stream>>>(
       *g, P, ldP, (const __half*)e16, F, carry, h_in, scale_h, shift_h, h_out, (__half*)h16_out, flags, chunk,
       node_begin, node_end, xp_ptr, xp_row, xp_buf, partial_out);

@@ -30,8 +30,7 @@ struct Score2Cfg {
 
 template <int H, int HS>
 __global__ void __launch_bounds__(kS2Threads, 1)
-score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                         gnb_graph_t g, const float* __restrict__ S, const __half* __restrict__ Wp,
+score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g, const float* __restrict__ S, const __half* __restrict__ Wp,
                          const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
                          const float* __restrict__ b3, float* __restrict__ scores) {
   using C = Score2Cfg<H, HS>;
@@ -70,8 +69,7 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
       mbar_init(&dempty[i], 8);
     }
     fence_barrier_init();
-    prefetch_tensormap(&map_hi);
-    prefetch_tensormap(&map_lo);
+    prefetch_tensormap(&map_e);
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
@@ -105,8 +103,8 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_hi, const __gri
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
         for (int kb = 0; kb < T::KBLOCKS; ++kb) {
-          tma_load_2d(stage + kb * T::KB_BYTES, &map_hi, kb * kKB, (int)(t * kS2NT), &full[s]);
-          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_lo, kb * kKB, (int)(t * kS2NT), &full[s]);
+          tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kS2NT), &full[s]);
+          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kS2NT), &full[s]);
         }
       }
       if (t + workers < num_tiles) load_idx(t + workers, nxt);
@@ -227,15 +225,13 @@ static int score_forward_tc2_impl(const gnb_graph_t* g, const float* S, const vo
     return (int)err;
   }
   const int64_t E = g->num_edges;
-  CUtensorMap map_hi, map_lo;
-  int rc = make_image_map(&map_hi, e16, E, H, kS2NT);
-  if (rc) return rc;
-  rc = make_image_map(&map_lo, (const __half*)e16 + E * H, E, H, kS2NT);
+  CUtensorMap map_e;
+  int rc = make_state_map(&map_e, e16, E, H, kS2NT);
   if (rc) return rc;
   const int64_t num_tiles = (E + kS2NT - 1) / kS2NT;
   int64_t grid = sm_count();
   if (grid > num_tiles) grid = num_tiles;
-  score_forward_tc2_kernel<H, HS><<<(unsigned)grid, kS2Threads, C::SMEM, stream>>>(map_hi, map_lo, *g, S, (const __half*)Wp,
+  score_forward_tc2_kernel<H, HS><<<(unsigned)grid, kS2Threads, C::SMEM, stream>>>(map_e, *g, S, (const __half*)Wp,
                                                                                   W2, b2, W3, b3, scores);
   return check_launch("gnb_score_forward_tc2");
 }

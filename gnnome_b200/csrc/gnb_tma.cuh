@@ -1,12 +1,12 @@
 // TMA (cp.async.bulk.tensor) + 128-byte-swizzled operand tiles for the second-generation tensor-core kernels.
 //
-// State layout in HBM ("split16"): a matrix X[rows][K] of fp32 values is held as TWO row-major fp16 images,
-//   hi[r][k] = fp16(x / 16),  lo[r][k] = fp16(x / 16 - hi[r][k])           (x ~ 16 * (hi + lo), 22 significant bits)
-// at base and base + rows * K halves.  It is the same 4 bytes per element as fp32, but the images ARE the
-// tcgen05 operands: a tile of NT rows is brought into shared memory by the TMA engine (no conversion
-// instructions, no registers in flight), one [NT rows][64 halves = 128 bytes] box per 64-channel block and
-// image, written in the SWIZZLE_128B pattern the UMMA shared-memory descriptor expects, and e' / h' go back
-// with TMA stores from the same shared-memory tile.
+// State layout in HBM ("split16"): a matrix X[rows][K] of fp32 values is held as fp16 pairs, row r =
+//   [ hi[r][0..K) | lo[r][0..K) ],  hi = fp16(x / 16),  lo = fp16(x / 16 - hi)     (x ~ 16 * (hi + lo), 22 significant bits)
+// i.e. one row-major fp16 matrix [rows][2K]: the same 4 bytes per element as fp32 and a row is still one contiguous
+// piece of memory (the reverse aggregation gathers whole rows), but the two halves ARE the tcgen05 operands: a
+// tile of NT rows is brought into shared memory by the TMA engine (no conversion instructions, no registers in
+// flight), one [NT rows][64 halves = 128 bytes] box per 64-channel block and half, written in the SWIZZLE_128B
+// pattern the UMMA shared-memory descriptor expects, and e' / h' go back with TMA stores from the same tile.
 #pragma once
 
 #include <cuda.h>
@@ -33,9 +33,10 @@ struct Tile2 {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// 2-D tensor map over one fp16 image [rows][K] (row-major), box = [box_rows][64 halves], SWIZZLE_128B,
-// out-of-bounds rows read as zeros (loads) / are clipped (stores).  Returns 0 or a negative GNB_E_* code.
-int make_image_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows);
+// 2-D tensor map over a split16 matrix [rows][2K] fp16 (hi columns [0, K), lo columns [K, 2K)), box =
+// [box_rows][64 halves], SWIZZLE_128B; out-of-bounds rows read as zeros (loads) / are clipped (stores).
+// Returns 0 or a negative GNB_E_* code.
+int make_state_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows);
 
 // ---------------------------------------------------------------------------------------------
 // device side

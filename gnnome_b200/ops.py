@@ -189,17 +189,17 @@ def scatter_rows(x, idx, out=None):
 
 
 # ------------------------------------------------------------------------------------------------
-# split16 path (TMA-fed tcgen05 kernels): state = fp16 images [2][rows][K] (hi, lo), x = 16 * (hi + lo)
+# split16 path (TMA-fed tcgen05 kernels): state = fp16 [rows][2][K] (row = hi | lo), x = 16 * (hi + lo)
 # ------------------------------------------------------------------------------------------------
 def _img(t, name):
-    if t.dtype != torch.float16 or not t.is_cuda or not t.is_contiguous() or t.ndim != 3 or t.shape[0] != 2:
-        raise ValueError(f'{name} must be a contiguous float16 CUDA tensor of shape [2][rows][K] (got {t.dtype}, '
+    if t.dtype != torch.float16 or not t.is_cuda or not t.is_contiguous() or t.ndim != 3 or t.shape[1] != 2:
+        raise ValueError(f'{name} must be a contiguous float16 CUDA tensor of shape [rows][2][K] (got {t.dtype}, '
                          f'{tuple(t.shape)}, {t.device})')
     return t.data_ptr()
 
 
 def empty_split16(rows, K, device):
-    return torch.empty((2, rows, K), dtype=torch.float16, device=device)
+    return torch.empty((rows, 2, K), dtype=torch.float16, device=device)
 
 
 def split_rows(x, idx=None, out=None):
@@ -218,7 +218,7 @@ def split_rows(x, idx=None, out=None):
 def merge_rows(x16, idx=None, out=None):
     """split16 images -> fp32 rows; ``out[idx[r]] = merge(x16[r])`` when ``idx`` is given."""
     lib = _lib.load()
-    _, rows, K = x16.shape
+    rows, _, K = x16.shape
     if out is None:
         out = torch.empty((rows, K), dtype=torch.float32, device=x16.device)
     with _logged('gnb_merge_rows', x16.device):
@@ -244,7 +244,7 @@ def encode2(x, idx, W1, b1, W2t, b2, rows, want16=True, want32=False):
 def node_linear_tc2(x16, Wp, bias, M, out=None):
     """out = X @ W.T + bias with X in split16 format; Wp = pack_linear_tc(W[M][K])."""
     lib = _lib.load()
-    _, rows, K = x16.shape
+    rows, _, K = x16.shape
     if out is None:
         out = torch.empty((rows, M), dtype=torch.float32, device=x16.device)
     with _logged('gnb_node_linear_tc2', x16.device):

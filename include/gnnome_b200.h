@@ -171,13 +171,13 @@ int gnb_scatter_rows(const float* in, const int32_t* idx, int64_t rows, int W, f
                      void* stream);
 
 /* ---- split16 path: TMA-fed tcgen05 kernels (the product path for H in {64, 128, 256}) ------------------
- * Edge and node state is held in HBM as TWO row-major fp16 images per matrix X[rows][K],
- *   hi[r][k] = fp16(x / 16),  lo[r][k] = fp16(x / 16 - hi[r][k])     (x ~ 16 * (hi + lo), 22 significant bits),
- * hi at the base pointer, lo at base + rows * K halves: 4 bytes per element like fp32, but the images are the
- * tensor-core operands, so tiles go HBM -> shared memory -> MMA through the TMA engine with no conversion
- * instructions, and the updated state goes back with TMA stores. */
+ * Edge and node state X[rows][K] is held in HBM as one row-major fp16 matrix [rows][2K], row r =
+ *   [ hi[r][0..K) | lo[r][0..K) ],  hi = fp16(x / 16),  lo = fp16(x / 16 - hi)     (x ~ 16 * (hi + lo), 22 significant bits):
+ * 4 bytes per element like fp32 and a row is still contiguous, but the two halves are the tensor-core operands,
+ * so tiles go HBM -> shared memory -> MMA through the TMA engine with no conversion instructions, and the updated
+ * state goes back with TMA stores. */
 
-/* Bytes of the split16 images of a [rows][K] matrix. */
+/* Bytes of the split16 form of a [rows][K] matrix. */
 size_t gnb_split16_bytes(int64_t rows, int K);
 
 /* out16[r] = split(in[idx ? idx[r] : r])   (fp32 rows -> images; idx = gnb_graph_t.in_eid moves edge rows from
@@ -201,6 +201,10 @@ int gnb_node_linear_tc2(const void* X16, int64_t rows, int K, const void* Wp, co
 int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
                          const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
                          int32_t* tile_flags, int epoch, int flags, void* stream);
+
+/* Debugging aid: buf = device uint64[SMs][32 warps][5] (or NULL to switch off); every epilogue warp of
+ * gnb_edge_forward_tc2 then leaves its cycle accounting there (full wait, accumulator wait, compute, hand-off, tiles). */
+void gnb_debug_edge_timing(void* buf);
 
 /* gnb_node_update with e' read from split16 images; writes h' as fp32 rows (h_out, row i) and, if h16_out is
  * not NULL, as split16 images of the rows node_begin .. node_end (row i - node_begin) for the next layer's
