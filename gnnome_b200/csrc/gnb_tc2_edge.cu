@@ -27,7 +27,8 @@ namespace tc {
 
 constexpr int kE2NT = 64;        // edges per tile (MMA N)
 constexpr int kE2Chunk = 32;     // edges per epilogue warp = carry granularity
-constexpr int kE2Groups = 2;     // epilogue groups = accumulator buffers
+constexpr int kE2Groups = 2;     // epilogue groups
+constexpr int kE2DBufs = 4;      // accumulator buffers (two per group: the MMA of a group's next tile overlaps its epilogue)
 constexpr int kE2FirstEpiWarp = 4;
 constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 8 * kE2Groups);
 constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[64], dst[64], prev_dst, next_dst
@@ -42,7 +43,7 @@ struct Edge2Cfg {
   // epilogue warps of a group that own live channels (the others idle: they must not feed the barriers, or they
   // would run ahead of the live ones and complete a phase early)
   static constexpr int LIVE_WARPS = 2 * (HC / 32);
-  static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + kE2Groups * kE2NT);
+  static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + kE2DBufs * kE2NT);
   static constexpr uint32_t D_COL0 = 2 * T::W_COLS;
   static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 256;
 };
@@ -64,7 +65,7 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
-template <int H, bool kTiming>
+template <int H, bool kResidual, bool kTiming>
 __global__ void __launch_bounds__(kE2Threads, 1)
 edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ Wp,
                         const float* __restrict__ scale_e, const float* __restrict__ shift_e,
@@ -78,9 +79,9 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   uint64_t* bars = reinterpret_cast<uint64_t*>(idx_area + C::NB * kE2IdxInts);
   uint64_t* full = bars;                    // [NB] producer (TMA bytes + 32 index lanes) -> MMA, epilogue
   uint64_t* empty = full + C::NB;           // [NB] store warp -> producer
-  uint64_t* dfull = empty + C::NB;          // [G]  MMA -> epilogue
-  uint64_t* dempty = dfull + kE2Groups;     // [G]  epilogue -> MMA
-  uint64_t* sfull = dempty + kE2Groups;     // [G]  epilogue (e' written into the stage) -> store warp
+  uint64_t* dfull = empty + C::NB;          // [D]  MMA -> epilogue
+  uint64_t* dempty = dfull + kE2DBufs;      // [D]  epilogue -> MMA
+  uint64_t* sfull = dempty + kE2DBufs;      // [G]  epilogue (e' written into the stage) -> store warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + kE2Groups);
 
   const int half = blockIdx.x % C::NH, worker = blockIdx.x / C::NH;
@@ -93,11 +94,11 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       mbar_init(&full[i], 33);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < kE2Groups; ++i) {
+    for (int i = 0; i < kE2DBufs; ++i) {
       mbar_init(&dfull[i], 1);
       mbar_init(&dempty[i], C::LIVE_WARPS);
-      mbar_init(&sfull[i], C::LIVE_WARPS);
     }
+    for (int i = 0; i < kE2Groups; ++i) mbar_init(&sfull[i], C::LIVE_WARPS);
     fence_barrier_init();
     prefetch_tensormap(&map_e);
   }
@@ -172,12 +173,12 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     // ---------------------------------------------------------------- MMA issue
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
-      const int s = i % C::NB, d = i % kE2Groups;
+      const int s = i % C::NB, d = i % kE2DBufs;
       mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
       // both channel halves read whole rows of e and overwrite their own half in place: tell the other half
       // that this CTA's copy of tile t has left global memory
       if (C::NH > 1 && lane == 0) red_release_add2(tile_flags + t, 1);
-      mbar_wait_sleep(&dempty[d], ((i / kE2Groups) & 1) ^ 1, 32);
+      mbar_wait_sleep(&dempty[d], ((i / kE2DBufs) & 1) ^ 1, 32);
       tc_fence_after();
       if (lane == 0) {
         issue_tile_mma_sw128<H, kE2NT>(tmem_base, tmem_base + C::D_COL0 + d * kE2NT,
@@ -221,7 +222,6 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     const int c = half * C::HC + (ch_ok ? cl : 0);
     const int64_t my_tiles = ch_ok ? num_tiles : 0;   // warps without live channels (H = 64) sit the loop out
     const float sc = scale_e[c], sh = shift_e[c];
-    const bool residual = flags & GNB_F_RESIDUAL;
     const char* Pc = reinterpret_cast<const char*>(P + 2 * c);        // (B1h[c], A2h[c]) interleaved
     const char* Pb2 = reinterpret_cast<const char*>(P + 2 * H + c);   // B2h[c]
     const int ldPb = (int)(ldP * (int64_t)sizeof(float));            // row pitch in bytes (< 2^31, checked by the host)
@@ -245,7 +245,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     int i = 0;
     for (int64_t t = worker; t < my_tiles; t += workers, ++i) {
       if (i % kE2Groups != grp) continue;
-      const int s = i % C::NB;
+      const int s = i % C::NB, d = i % kE2DBufs;
+      const uint32_t dpar = (i / kE2DBufs) & 1;
       const int64_t cs = t * kE2NT + sub * kE2Chunk;
       const bool live = cs < E;              // warp-uniform; false only for the second half of a ragged last tile
       const int n = live ? (int)((E - cs < kE2Chunk) ? (E - cs) : kE2Chunk) : 0;
@@ -253,16 +254,15 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);  // indices published (and the operand tile has landed)
       const long long t1 = kTiming ? clock64() : 0;
       if (!live) {  // nothing to compute, but the barriers still have to be fed
-        mbar_wait_sleep(&dfull[grp], (i / kE2Groups) & 1);
+        mbar_wait_sleep(&dfull[d], dpar);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&dempty[grp]);
+        if (lane == 0) mbar_arrive(&dempty[d]);
         stage_done();
         continue;
       }
       const int* ia = idx_area + s * kE2IdxInts;
-      const int my_src = ia[sub * kE2Chunk + lane];
       const int my_dst = ia[kE2NT + sub * kE2Chunk + lane];
       const int prev_dst = (sub == 0) ? ia[2 * kE2NT] : ia[kE2NT + kE2Chunk - 1];
       const int next_dst = (sub == 0) ? ia[kE2NT + kE2Chunk] : ia[2 * kE2NT + 1];
@@ -277,25 +277,33 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 
       const int64_t chunk = cs / kE2Chunk;
       const uint32_t st_hi = smem_u32(bufs + (size_t)s * T::BUF_BYTES) + col_base;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + grp * kE2NT + sub * kE2Chunk;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + d * kE2NT + sub * kE2Chunk;
       int cur = -1;
       float num = 0.f, den = 0.f;
 
-      // Software pipeline over four batches of eight edges: the gathers of batch b+1 -- fa = (B1h, A2h)[src] and
-      // fb = B2h[dst], one coalesced row segment per warp each -- are in flight while batch b is computed.
-      // A batch is computed in two passes: (1) branch-free, eight edges interleaved: z -> e' -> split fp16 -> stage,
-      // sigma; (2) the per-destination bookkeeping, a straight sum when no segment opens inside the batch.
+      // Software pipeline over four batches of eight edges: the gathers of batch b+1 -- xa = (B1h, A2h)[src] and
+      // xb = B2h[dst], one coalesced row segment per warp each -- are in flight while batch b is computed.
       constexpr int kEB = 8;
-      const int my_dst_c = my_dst < 0 ? 0 : my_dst;   // rows past the end of a ragged tile: any valid address
+      const int* ia_src = ia + sub * kE2Chunk;            // endpoints of the chunk's 32 edges: warp-uniform reads
+      const int* ia_dst = ia + kE2NT + sub * kE2Chunk;
       auto fetch = [&](int b, float2 (&xa)[kEB], float (&xb)[kEB]) {
+        int sj[kEB], dj[kEB];
+        *reinterpret_cast<int4*>(&sj[0]) = *reinterpret_cast<const int4*>(ia_src + b * kEB);
+        *reinterpret_cast<int4*>(&sj[4]) = *reinterpret_cast<const int4*>(ia_src + b * kEB + 4);
+        *reinterpret_cast<int4*>(&dj[0]) = *reinterpret_cast<const int4*>(ia_dst + b * kEB);
+        *reinterpret_cast<int4*>(&dj[4]) = *reinterpret_cast<const int4*>(ia_dst + b * kEB + 4);
 #pragma unroll
         for (int u = 0; u < kEB; ++u) {
-          const int sj = __shfl_sync(kFull, my_src, b * kEB + u);
-          const int dj = __shfl_sync(kFull, my_dst_c, b * kEB + u);
-          xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj * ldPb));
-          xb[u] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj * ldPb));
+          xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj[u] * ldPb));
+          xb[u] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)max(dj[u], 0) * ldPb));   // -1: past a ragged end
         }
       };
+      // Stage address of row r of the chunk for this thread's channel: st_hi + r * 128 + (((c%64)/8 ^ r%8) << 4).
+      // rowx[w] covers rows = w (mod 4) of the current half-batch; it advances by 4 rows per half-batch, which
+      // flips bit 2 of the swizzle term (xor 64 bytes) on top of the 512-byte step.
+      uint32_t rowx[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) rowx[w] = st_hi + (uint32_t)(w * 128) + ((col_x ^ (uint32_t)w) << 4);
       auto compute = [&](int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
         // Two half-batches of four edges.  The shared-memory accesses are volatile asm statements, which the
         // compiler keeps in program order: the loads of a half-batch come first and its stores last, so that the
@@ -308,9 +316,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             ein[w] = 0.f;
-            if (residual) {   // row (b*8 + hb + w) of the chunk: row % 8 == hb + w
-              const uint32_t a = st_hi + (uint32_t)((b * kEB + hb + w) * 128) + ((col_x ^ (uint32_t)(hb + w)) << 4);
-              const __half_raw hr{lds_u16(a)}, lr{lds_u16(a + T::IMG_BYTES)};
+            if (kResidual) {
+              const __half_raw hr{lds_u16(rowx[w])}, lr{lds_u16(rowx[w] + T::IMG_BYTES)};
               ein[w] = (__half2float(__half(hr)) + __half2float(__half(lr))) * kWScale;
             }
           }
@@ -318,26 +325,33 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           if (b == kE2Chunk / kEB - 1 && hb == 4) {   // last read of this accumulator buffer: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&dempty[grp]);
+            if (lane == 0) mbar_arrive(&dempty[d]);
           }
-          float sg[4];
-          uint32_t pk[4];
+          float v[4], sg[4];
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const int u = hb + w;
-            const float v = fmaxf(fmaf(__uint_as_float(zr[w]) + xa[u].x + xb[u], sc, sh), 0.f) + ein[w];
-            __half nh, nl;
-            split1(v, nh, nl);
-            pk[w] = (uint32_t)__half_raw(nh).x | ((uint32_t)__half_raw(nl).x << 16);
-            sg[w] = (b * kEB + u < n) ? sigmoidf_fast(v) : 0.f;
+            v[w] = fmaxf(fmaf(__uint_as_float(zr[w]) + xa[u].x + xb[u], sc, sh), 0.f) + ein[w];
+            sg[w] = (b * kEB + u < n) ? sigmoidf_fast(v[w]) : 0.f;
+          }
+          // split fp16: two edges per packed conversion
+          uint32_t ph[2], pl[2];
+#pragma unroll
+          for (int w2 = 0; w2 < 2; ++w2) {
+            const float x0 = v[2 * w2] * kXScale, x1 = v[2 * w2 + 1] * kXScale;
+            const __half2 hh = __floats2half2_rn(x0, x1);
+            const float2 back = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
+            ph[w2] = *reinterpret_cast<const uint32_t*>(&hh);
+            pl[w2] = *reinterpret_cast<const uint32_t*>(&ll);
           }
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             if (b * kEB + hb + w < n) {
-              const uint32_t a = st_hi + (uint32_t)((b * kEB + hb + w) * 128) + ((col_x ^ (uint32_t)(hb + w)) << 4);
-              sts_u16(a, (uint16_t)(pk[w] & 0xffffu));
-              sts_u16(a + T::IMG_BYTES, (uint16_t)(pk[w] >> 16));
+              sts_u16(rowx[w], (uint16_t)((w & 1) ? (ph[w >> 1] >> 16) : (ph[w >> 1] & 0xffffu)));
+              sts_u16(rowx[w] + T::IMG_BYTES, (uint16_t)((w & 1) ? (pl[w >> 1] >> 16) : (pl[w >> 1] & 0xffffu)));
             }
+            rowx[w] = (rowx[w] + 512u) ^ 64u;
           }
           const unsigned mb = (segmask >> (b * kEB + hb)) & 0xfu;
           if (mb == 0) {                 // warp-uniform: the four edges continue the running segment
@@ -358,7 +372,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
                     F[(int64_t)cur * H + c] = gate_div(num, den);
                   }
                 }
-                cur = __shfl_sync(kFull, my_dst, b * kEB + hb + w);
+                cur = ia_dst[b * kEB + hb + w];
                 num = 0.f;
                 den = 0.f;
               }
@@ -372,7 +386,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       float fb0[kEB], fb1[kEB];
       fetch(0, fa0, fb0);
       const long long t2 = kTiming ? clock64() : 0;
-      mbar_wait_sleep(&dfull[grp], (i / kE2Groups) & 1, 32);
+      mbar_wait_sleep(&dfull[d], dpar, 32);
       tc_fence_after();
       const long long t3 = kTiming ? clock64() : 0;
 #pragma unroll 1
@@ -419,7 +433,9 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
                                  const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
                                  int32_t* tile_flags, int epoch, int flags, cudaStream_t stream) {
   using C = Edge2Cfg<H>;
-  auto kern = g_edge_timing ? edge_forward_tc2_kernel<H, true> : edge_forward_tc2_kernel<H, false>;
+  const bool res = flags & GNB_F_RESIDUAL;
+  auto kern = g_edge_timing ? (res ? edge_forward_tc2_kernel<H, true, true> : edge_forward_tc2_kernel<H, false, true>)
+                            : (res ? edge_forward_tc2_kernel<H, true, false> : edge_forward_tc2_kernel<H, false, false>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (err != cudaSuccess) {
     set_error("gnb_edge_forward_tc2: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(err));
