@@ -310,6 +310,10 @@ def run_gpu_arm(args, wl):
                'includes': 'per rank: H2D of its shard (local src/dst, x, e), graph staging, forward with halo '
                            'exchanges, D2H of its scores; max over ranks'}
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- CPU baseline + parity on the bounded sample (rank 0, N=1 only) ------------------------
