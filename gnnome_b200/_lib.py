@@ -51,6 +51,7 @@ SIGNATURES = {
     'gnb_merge_rows': (_I, [_P, _P, _L, _I, _P, _P]),
     'gnb_encode2': (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'gnb_node_linear_tc2': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
+    'gnb_edge_tile_tc2': (_I, [_I]),
     'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     'gnb_debug_edge_timing': (None, [_P]),
     'gnb_node_update2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),

@@ -5,15 +5,16 @@
 //   F_i  = sum_{p: dst_p = i} sigmoid(e'_p) * A2h[src_p] / (sum_p sigmoid(e'_p) + 1e-6)
 //
 // Persistent CTAs, one per SM; a CTA owns HC = min(H, 128) output channels (H = 256: the two channel halves of a
-// tile run on neighbouring CTAs) with its W_B3 block resident in TMEM, and walks 64-edge tiles of the dst-sorted
-// edge array.  One shared-memory stage serves a tile through its whole life:
+// tile run on neighbouring CTAs) with its W_B3 block resident in TMEM, and walks 32-edge tiles of the dst-sorted
+// edge array (six to eight stages in flight: one per epilogue group plus the tiles being loaded / multiplied ahead).
+// One shared-memory stage serves a tile through its whole life:
 //   TMA load (hi, lo images, 128B-swizzled)  ->  MMA B operand  ->  residual source for the epilogue  ->
 //   e' written over it in place (same thread, same address)  ->  TMA store back to HBM.
 //   warp 0      : producer: TMA loads (lane 0) + the tile's (src, dst) indices into the stage's index area
 //   warp 1      : MMA issue (one lane)
-//   warps 2, 3  : TMA store of group 0 / 1 (wait for the group's epilogue, H = 256: for the other channel half
-//                 to have loaded the tile, store, release the stage)
-//   warps 4..19 : epilogue, 2 groups (= accumulator buffers) x 4 TMEM lane quarters x 2 chunks of 32 edges.
+//   warps 2, 3  : TMA stores, one thread per epilogue group (wait for the group's epilogue, H = 256: for the other
+//                 channel half to have loaded the tile, store, release the stage)
+//   warps 4..19 : epilogue, 4 groups x 4 TMEM lane quarters; group g takes tiles g, g+4, ... (one 32-edge chunk).
 //                 A thread owns ONE channel and walks its 32 consecutive edges: gathers of the (B1h, A2h) node
 //                 rows are coalesced across the warp, per-destination sums are register accumulators closed at
 //                 warp-uniform segment boundaries (no atomics, fixed summation order).  Segments that straddle
@@ -25,27 +26,28 @@
 namespace gnb {
 namespace tc {
 
-constexpr int kE2NT = 64;        // edges per tile (MMA N)
-constexpr int kE2Chunk = 32;     // edges per epilogue warp = carry granularity
-constexpr int kE2Groups = 2;     // epilogue groups
-constexpr int kE2DBufs = 4;      // accumulator buffers (two per group: the MMA of a group's next tile overlaps its epilogue)
+constexpr int kE2NT = 32;        // edges per tile (MMA N) = edges per epilogue warp = carry granularity
+constexpr int kE2Chunk = kE2NT;
+constexpr int kE2Groups = 4;     // epilogue groups of four warps (one per TMEM lane quarter); group g takes tiles g, g+4, ...
+constexpr int kE2DBufs = 8;      // accumulator buffers (two per group: the MMA of a group's next tile overlaps its epilogue)
 constexpr int kE2FirstEpiWarp = 4;
-constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 8 * kE2Groups);
-constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[64], dst[64], prev_dst, next_dst
+constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 4 * kE2Groups);
+constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[32], dst[32], prev_dst, next_dst (+ pad: stages stay 16-byte aligned)
 
 template <int H>
 struct Edge2Cfg {
   static constexpr int HC = H < kM ? H : kM;   // live channels per CTA
   static constexpr int NH = H / HC;            // channel halves (CTAs per tile)
   using T = Tile2<H, kE2NT>;
-  // NB <= 2 * groups: an epilogue group can never run two tiles ahead of its store warp (see sfull)
-  static constexpr int NB = (H >= 256) ? 3 : 4;
+  // Stages: one per group in its epilogue plus two being loaded / multiplied ahead.  NB <= 2 * groups: an epilogue
+  // group can never run two tiles ahead of its store warp (see sfull).
+  static constexpr int NB = (H >= 256) ? 6 : 8;
   // epilogue warps of a group that own live channels (the others idle: they must not feed the barriers, or they
   // would run ahead of the live ones and complete a phase early)
-  static constexpr int LIVE_WARPS = 2 * (HC / 32);
+  static constexpr int LIVE_WARPS = HC / 32;
   static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + kE2DBufs * kE2NT);
   static constexpr uint32_t D_COL0 = 2 * T::W_COLS;
-  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 256;
+  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 512;
 };
 
 __device__ __forceinline__ void red_release_add2(int32_t* p, int v) {
@@ -115,23 +117,20 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer: TMA + indices
-    auto load_idx = [&](int64_t t, int (&r)[5]) {
-      const int64_t p0 = t * kE2NT + lane, p1 = p0 + 32;
+    auto load_idx = [&](int64_t t, int (&r)[3]) {
+      const int64_t p0 = t * kE2NT + lane;
       r[0] = (p0 < E) ? g.in_src[p0] : 0;
-      r[1] = (p1 < E) ? g.in_src[p1] : 0;
-      r[2] = (p0 < E) ? g.in_dst[p0] : -1;
-      r[3] = (p1 < E) ? g.in_dst[p1] : -1;
-      r[4] = -1;
-      if (lane == 0 && t > 0) r[4] = g.in_dst[t * kE2NT - 1];
-      if (lane == 1 && (t + 1) * kE2NT < E) r[4] = g.in_dst[(t + 1) * kE2NT];
+      r[1] = (p0 < E) ? g.in_dst[p0] : -1;
+      r[2] = -1;
+      if (lane == 0 && t > 0) r[2] = g.in_dst[t * kE2NT - 1];
+      if (lane == 1 && (t + 1) * kE2NT < E) r[2] = g.in_dst[(t + 1) * kE2NT];
     };
     // Every node row is touched for the first time by SOME gather of the epilogue, and that one would wait for
     // HBM; the producer knows the tile's endpoints two to three tile periods before the epilogue needs them, so
     // it pulls this CTA's slices of the (B1h, A2h)[src] and B2h[dst] rows into L2 ahead of time.
-    auto prefetch_rows = [&](const int (&r)[5]) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int sj = r[k], dj = r[2 + k];
+    auto prefetch_rows = [&](const int (&r)[3]) {
+      {
+        const int sj = r[0], dj = r[1];
         if (dj >= 0) {
           const char* a = reinterpret_cast<const char*>(P + (int64_t)sj * ldP + 2 * half * C::HC);
 #pragma unroll
@@ -142,14 +141,14 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         }
       }
     };
-    int cur[5], nxt[5];
+    int cur[3], nxt[3];
     if (worker < num_tiles) load_idx(worker, cur);
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
       prefetch_rows(cur);
       mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
-      if (lane == 0) {
+      if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
@@ -161,13 +160,11 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (t + workers < num_tiles) load_idx(t + workers, nxt);   // in flight while this tile's indices are published
       int* ia = idx_area + s * kE2IdxInts;
       ia[lane] = cur[0];
-      ia[32 + lane] = cur[1];
-      ia[kE2NT + lane] = cur[2];
-      ia[kE2NT + 32 + lane] = cur[3];
-      if (lane < 2) ia[2 * kE2NT + lane] = cur[4];
+      ia[kE2NT + lane] = cur[1];
+      if (lane < 2) ia[2 * kE2NT + lane] = cur[2];
       mbar_arrive(&full[s]);
 #pragma unroll
-      for (int k = 0; k < 5; ++k) cur[k] = nxt[k];
+      for (int k = 0; k < 3; ++k) cur[k] = nxt[k];
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issue
@@ -180,7 +177,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (C::NH > 1 && lane == 0) red_release_add2(tile_flags + t, 1);
       mbar_wait_sleep(&dempty[d], ((i / kE2DBufs) & 1) ^ 1, 32);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         issue_tile_mma_sw128<H, kE2NT>(tmem_base, tmem_base + C::D_COL0 + d * kE2NT,
                                        smem_u32(bufs + (size_t)s * T::BUF_BYTES));
         mma_commit(&dfull[d]);
@@ -189,14 +186,17 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     }
   } else if (warp < kE2FirstEpiWarp) {
     // ---------------------------------------------------------------- TMA store of one epilogue group
-    const int grp = warp - 2;
-    if (lane == 0) {
-      int i = 0, j = 0;
+    // One store THREAD per epilogue group (lanes 0 and 16 of warps 2 and 3).  A group's phases of sfull are then
+    // consumed strictly in order by a thread that waits on nothing but that group, and since the producer loads
+    // tiles in order and NB <= 8, a group can never complete two phases ahead of its store thread (which would alias
+    // the phase parity and dead-lock) -- it could if two groups shared one store thread and one of them lagged.
+    if ((lane & 15) == 0) {
+      const int grp = (warp - 2) * 2 + (lane >> 4);
+      int i = 0;
       for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
         if (i % kE2Groups != grp) continue;
         const int s = i % C::NB;
-        mbar_wait_sleep(&sfull[grp], j & 1);
-        ++j;
+        mbar_wait_sleep(&sfull[grp], (i / kE2Groups) & 1);
         if (C::NH > 1) {  // the other half must have read tile t before our channels of it are overwritten
           while (ld_acquire2(tile_flags + t) < C::NH * epoch) __nanosleep(32);
         }
@@ -216,7 +216,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   } else {
     // ---------------------------------------------------------------- epilogue
     const int ew = warp - kE2FirstEpiWarp;
-    const int grp = ew >> 3, sub = (ew >> 2) & 1, q = warp & 3;
+    const int grp = ew >> 2, q = warp & 3;
+    constexpr int sub = 0;                   // one 32-edge chunk per tile
     const int cl = q * 32 + lane;            // TMEM lane = channel within the CTA's block
     const bool ch_ok = cl < C::HC;           // warp-uniform (HC is a multiple of 32)
     const int c = half * C::HC + (ch_ok ? cl : 0);
@@ -264,8 +265,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       }
       const int* ia = idx_area + s * kE2IdxInts;
       const int my_dst = ia[kE2NT + sub * kE2Chunk + lane];
-      const int prev_dst = (sub == 0) ? ia[2 * kE2NT] : ia[kE2NT + kE2Chunk - 1];
-      const int next_dst = (sub == 0) ? ia[kE2NT + kE2Chunk] : ia[2 * kE2NT + 1];
+      const int prev_dst = ia[2 * kE2NT];
+      const int next_dst = ia[2 * kE2NT + 1];
       int head_dst = -1, tail_dst = -1;
       const int up = __shfl_up_sync(kFull, my_dst, 1);
       // bit j: edge j of the chunk opens a new destination segment
@@ -459,6 +460,8 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
 }  // namespace gnb
 
 using namespace gnb;
+
+extern "C" int gnb_edge_tile_tc2(int H) { return (H == 64 || H == 128 || H == 256) ? tc::kE2NT : GNB_E_INVALID; }
 
 extern "C" void gnb_debug_edge_timing(void* buf) { tc::g_edge_timing = (unsigned long long*)buf; }
 

@@ -72,11 +72,11 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      int i = 0;
-      for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
-        const int s = i % C::NB;
-        mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1);
+    int i = 0;
+    for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
+      const int s = i % C::NB;
+      mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
+      if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
@@ -85,16 +85,17 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
           tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_x, K + kb * kKB, (int)(t * kLin2NT), &full[s]);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issue
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB, d = i & 1;
-      mbar_wait(&full[s], (i / C::NB) & 1);
-      mbar_wait(&dempty[d], ((i >> 1) & 1) ^ 1);
+      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
+      mbar_wait_sleep(&dempty[d], ((i >> 1) & 1) ^ 1, 32);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         issue_tile_mma_sw128<K, kLin2NT>(tmem_base, tmem_base + C::D_COL0 + d * kLin2NT,
                                          smem_u32(bufs + (size_t)s * T::BUF_BYTES));
         mma_commit(&empty[s]);
@@ -111,7 +112,7 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       if ((i & 1) != g) continue;
-      mbar_wait(&dfull[g], (i >> 1) & 1);
+      mbar_wait_sleep(&dfull[g], (i >> 1) & 1, 32);
       tc_fence_after();
       uint32_t v0[32], v1[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + g * kLin2NT;

@@ -97,8 +97,8 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
-      mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1);
-      if (lane == 0) {
+      mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
+      if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
@@ -124,10 +124,10 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB, d = i % kS2Groups;
-      mbar_wait(&full[s], (i / C::NB) & 1);
-      mbar_wait(&dempty[d], ((i / kS2Groups) & 1) ^ 1);
+      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
+      mbar_wait_sleep(&dempty[d], ((i / kS2Groups) & 1) ^ 1, 32);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         issue_tile_mma_sw128<H, kS2NT>(tmem_base, tmem_base + C::D_COL0 + d * kS2NT,
                                        smem_u32(bufs + (size_t)s * T::BUF_BYTES));
         mma_commit(&empty[s]);
@@ -149,7 +149,7 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       if (i % kS2Groups != grp) continue;
       const int s = i % C::NB;
-      mbar_wait(&full[s], (i / C::NB) & 1);
+      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
       const int* ia = idx_area + s * kS2IdxInts;
       // copy what phase A / B need out of the stage's index area, then release our share of the stage
       const int my_src = ia[sub * 32 + lane];
@@ -157,7 +157,7 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
       const int b_eid = ia[2 * kS2NT + (gt >> 2)];
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
-      mbar_wait(&dfull[grp], (i / kS2Groups) & 1);
+      mbar_wait_sleep(&dfull[grp], (i / kS2Groups) & 1, 32);
       tc_fence_after();
       // ---- phase A: hidden layer 1 for this warp's 32 edges x 32 units ---------------------------------
       if (unit_ok) {

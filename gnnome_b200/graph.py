@@ -80,9 +80,10 @@ class GraphIndex:
     def num_chunks(self, H, backend='tc'):
         return max(1, -(-self.E // self.chunk(H, backend)))
 
-    def tile_flags(self, H):
-        """Zeroed int32[tiles] + launch counter for the H=256 channel-half handshake of gnb_edge_forward_tc."""
-        tile = _lib.load().gnb_edge_tile_tc(H)
+    def tile_flags(self, H, backend='tc'):
+        """Zeroed int32[tiles] + launch counter for the H=256 channel-half handshake of gnb_edge_forward_tc / _tc2."""
+        lib = _lib.load()
+        tile = lib.gnb_edge_tile_tc2(H) if backend == 'tc2' else lib.gnb_edge_tile_tc(H)
         st = self._tile_flags.get(tile)
         if st is None:
             st = self._tile_flags[tile] = [torch.zeros(max(1, -(-self.E // tile)), dtype=torch.int32,

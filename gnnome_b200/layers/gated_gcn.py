@@ -194,7 +194,7 @@ class _GatedGCNBase(nn.Module):
             h16_out = torch.empty_like(h16)
         flags = self._flags()
         ops.node_linear_tc2(h16, pk['Wn_t'], pk['bn'], n_blocks * H, out=P)
-        tile_flags, epoch = gi.tile_flags(H) if H > 128 else (None, 0)
+        tile_flags, epoch = gi.tile_flags(H, 'tc2') if H > 128 else (None, 0)
         ops.edge_forward_tc2(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e16, Fb, carry, tile_flags, epoch, flags)
         ops.node_update2(gi, H, P, e16, Fb, carry, h32, pk['scale_h'], pk['shift_h'], h_out, h16_out, flags,
                          gi.chunk(H, 'tc'))

@@ -171,8 +171,9 @@ class CudaKernels:
         return self.ops.gather_rows(table, idx, out=out)
 
     def edge_forward(self, gi, H, P, pk, e_pos, F, carry, flags):
-        tile_flags, epoch = gi.tile_flags(H) if H > 128 else (None, 0)
-        fn = self.ops.edge_forward_tc2 if e_pos.dtype == torch.float16 else self.ops.edge_forward_tc
+        tc2 = e_pos.dtype == torch.float16
+        tile_flags, epoch = gi.tile_flags(H, 'tc2' if tc2 else 'tc') if H > 128 else (None, 0)
+        fn = self.ops.edge_forward_tc2 if tc2 else self.ops.edge_forward_tc
         fn(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, F, carry, tile_flags, epoch, flags)
 
     def carry_shape(self, gi, H):

@@ -196,8 +196,12 @@ int gnb_encode2(const float* in, const int32_t* idx, int64_t rows, int in_f, int
 int gnb_node_linear_tc2(const void* X16, int64_t rows, int K, const void* Wp, const float* bias, int M,
                         float* out, int64_t ld_out, void* stream);
 
+/* Edges per tile of gnb_edge_forward_tc2 (tile_flags has ceil(E / this) entries). */
+int gnb_edge_tile_tc2(int H);
+
 /* gnb_edge_forward_tc with the edge state e16 in split16 format, updated in place (gated_gcn_full.py:97,104-114).
- * Same P / carry / tile_flags / epoch contract; carry granularity gnb_edge_chunk_tc(H). */
+ * Same P / carry / tile_flags / epoch contract (tile_flags sized with gnb_edge_tile_tc2); carry granularity
+ * gnb_edge_chunk_tc(H). */
 int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
                          const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
                          int32_t* tile_flags, int epoch, int flags, void* stream);

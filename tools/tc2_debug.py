@@ -156,7 +156,7 @@ def t_determinism():
                 ec = e16.clone()
                 Fb = torch.zeros((gi.N, H), device='cuda')
                 carry = torch.zeros((gi.num_chunks(H, 'tc'), 4, H), device='cuda')
-                tf, ep = gi.tile_flags(H) if H > 128 else (None, 0)
+                tf, ep = gi.tile_flags(H, 'tc2') if H > 128 else (None, 0)
                 ops.edge_forward_tc2(gi, H, P1, pk['We_t'], pk['scale_e'], pk['shift_e'], ec, Fb, carry, tf, ep, conv._flags())
                 torch.cuda.synchronize()
                 outs.append((ec, Fb, carry))
