@@ -50,6 +50,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The driver reads exactly ONE JSON line from stdout.  Libraries (NCCL prints its version banner on stdout) must
+# not get in the way: file descriptor 1 points at stderr for the whole run and the result line goes to the saved
+# original descriptor.
+_RESULT_FD = None
+
+
+def _protect_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def dist_env():
     return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 
@@ -127,6 +150,17 @@ def measured_peak():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_edge_traffic(workload, world):
+    """DRAM bytes of one launch of the aggregation kernel from the committed ncu capture (N=1 only)."""
+    if world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'edge_kernel_dram_traffic.json')) as f:
+            return json.load(f)['per_launch_bytes'].get(workload)
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def edge_kernel_bytes(n_nodes, n_edges, H):
     """Algorithmic (compulsory) bytes of ONE gnb_edge_forward launch, fp32 state, int32 indices:
     read e + write e' (2*E*H*4), read src/dst (8E), read the B1h/A2h/B2h node rows once each and
@@ -180,7 +214,7 @@ def run_reference_arm(args, wl):
         'e2e': {'value': value, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -261,7 +295,7 @@ def run_gpu_arm(args, wl):
         kb = edge_kernel_bytes(n_loc, m_loc, H)
         achieved = kb / (float(np.mean(ek)) * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'kernel': ek_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'frac': achieved / peak, 'traffic': measured_edge_traffic(args.workload, world), 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': kb, 'ms_per_launch': float(np.mean(ek)),
                     'whole_forward_frac': forward_bytes(n, m, H, L) / (ms * 1e-3) / 1e9 / peak / world}
 
@@ -343,7 +377,7 @@ def run_gpu_arm(args, wl):
         'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
         'kernels': breakdown,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -355,6 +389,7 @@ def main():
     ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
+    _protect_stdout()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
         run_reference_arm(args, wl)

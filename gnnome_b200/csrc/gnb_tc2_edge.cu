@@ -305,7 +305,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       uint32_t rowx[4];
 #pragma unroll
       for (int w = 0; w < 4; ++w) rowx[w] = st_hi + (uint32_t)(w * 128) + ((col_x ^ (uint32_t)w) << 4);
-      auto compute = [&](int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
+      auto compute = [&](auto full_tag, int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
+        constexpr bool kFullChunk = decltype(full_tag)::value;   // all 32 edges exist: no per-edge validity tests
         // Two half-batches of four edges.  The shared-memory accesses are volatile asm statements, which the
         // compiler keeps in program order: the loads of a half-batch come first and its stores last, so that the
         // four per-edge dependency chains in between interleave.
@@ -333,7 +334,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           for (int w = 0; w < 4; ++w) {
             const int u = hb + w;
             v[w] = fmaxf(fmaf(__uint_as_float(zr[w]) + xa[u].x + xb[u], sc, sh), 0.f) + ein[w];
-            sg[w] = (b * kEB + u < n) ? sigmoidf_fast(v[w]) : 0.f;
+            sg[w] = (kFullChunk || b * kEB + u < n) ? sigmoidf_fast(v[w]) : 0.f;
           }
           // split fp16: two edges per packed conversion
           uint32_t ph[2], pl[2];
@@ -348,7 +349,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           }
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            if (b * kEB + hb + w < n) {
+            if (kFullChunk || b * kEB + hb + w < n) {
               sts_u16(rowx[w], (uint16_t)((w & 1) ? (ph[w >> 1] >> 16) : (ph[w >> 1] & 0xffffu)));
               sts_u16(rowx[w] + T::IMG_BYTES, (uint16_t)((w & 1) ? (pl[w >> 1] >> 16) : (pl[w >> 1] & 0xffffu)));
             }
@@ -390,13 +391,17 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       mbar_wait_sleep(&dfull[d], dpar, 32);
       tc_fence_after();
       const long long t3 = kTiming ? clock64() : 0;
+      auto run_chunk = [&](auto full_tag) {
 #pragma unroll 1
-      for (int b = 0; b < kE2Chunk / kEB; b += 2) {
-        fetch(b + 1, fa1, fb1);
-        compute(b, fa0, fb0);
-        if (b + 2 < kE2Chunk / kEB) fetch(b + 2, fa0, fb0);
-        compute(b + 1, fa1, fb1);
-      }
+        for (int b = 0; b < kE2Chunk / kEB; b += 2) {
+          fetch(b + 1, fa1, fb1);
+          compute(full_tag, b, fa0, fb0);
+          if (b + 2 < kE2Chunk / kEB) fetch(b + 2, fa0, fb0);
+          compute(full_tag, b + 1, fa1, fb1);
+        }
+      };
+      if (n == kE2Chunk) run_chunk(std::true_type{});
+      else run_chunk(std::false_type{});
       const long long t4 = kTiming ? clock64() : 0;
       // close the segment that is still open at the end of the chunk
       if (cur == tail_dst) {
