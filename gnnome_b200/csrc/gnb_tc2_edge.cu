@@ -38,6 +38,11 @@ template <int H>
 struct Edge2Cfg {
   static constexpr int HC = H < kM ? H : kM;   // live channels per CTA
   static constexpr int NH = H / HC;            // channel halves (CTAs per tile)
+  // H = 256: the two channel halves of a tile form a 2-CTA cluster; each loads half of the tile's boxes and
+  // multicasts them to both, so the e tile is read from L2 / HBM once, and no inter-CTA flag is needed for the
+  // in-place update (a CTA stores its channels only after ITS stage is complete, i.e. after every box of the tile
+  // has been read from global memory on behalf of both)
+  static constexpr bool MC = NH == 2;
   using T = Tile2<H, kE2NT>;
   // Stages: one per group in its epilogue plus two being loaded / multiplied ahead.  NB <= 2 * groups: an epilogue
   // group can never run two tiles ahead of its store warp (see sfull).
@@ -94,7 +99,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::NB; ++i) {
       mbar_init(&full[i], 33);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], C::MC ? 2 : 1);   // multicast: both CTAs of the cluster write into a stage
     }
     for (int i = 0; i < kE2DBufs; ++i) {
       mbar_init(&dfull[i], 1);
@@ -106,7 +111,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (C::MC) cluster_sync_all();   // the peer's multicast must find initialised barriers
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp >= kE2FirstEpiWarp && warp < kE2FirstEpiWarp + 4)
@@ -153,8 +159,13 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
         for (int kb = 0; kb < T::KBLOCKS; ++kb) {
-          tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s]);
-          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s]);
+          if (C::MC) {   // rank 0 brings the hi halves, rank 1 the lo halves, for both CTAs
+            tma_load_2d_mc(stage + half * T::IMG_BYTES + kb * T::KB_BYTES, &map_e, half * H + kb * kKB, (int)(t * kE2NT),
+                           &full[s], (uint16_t)3);
+          } else {
+            tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s]);
+            tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s]);
+          }
         }
       }
       if (t + workers < num_tiles) load_idx(t + workers, nxt);   // in flight while this tile's indices are published
@@ -174,7 +185,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
       // both channel halves read whole rows of e and overwrite their own half in place: tell the other half
       // that this CTA's copy of tile t has left global memory
-      if (C::NH > 1 && lane == 0) red_release_add2(tile_flags + t, 1);
+      if (C::NH > 1 && !C::MC && lane == 0) red_release_add2(tile_flags + t, 1);
       mbar_wait_sleep(&dempty[d], ((i / kE2DBufs) & 1) ^ 1, 32);
       tc_fence_after();
       if (elect_one()) {
@@ -197,7 +208,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         if (i % kE2Groups != grp) continue;
         const int s = i % C::NB;
         mbar_wait_sleep(&sfull[grp], (i / kE2Groups) & 1);
-        if (C::NH > 1) {  // the other half must have read tile t before our channels of it are overwritten
+        if (C::NH > 1 && !C::MC) {  // the other half must have read tile t before our channels of it are overwritten
           while (ld_acquire2(tile_flags + t) < C::NH * epoch) __nanosleep(32);
         }
         const uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
@@ -210,6 +221,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         tma_store_commit();
         tma_store_wait_read();
         mbar_arrive(&empty[s]);
+        if (C::MC) mbar_arrive_cluster(&empty[s], (uint32_t)(half ^ 1));   // the peer also writes into this stage
       }
       tma_store_wait_all();
     }
@@ -427,7 +439,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (C::MC) cluster_sync_all();   // the peer may still multicast into this CTA's stages / arrive on its barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
@@ -456,8 +469,24 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
   int workers = sm_count() / C::NH;
   if (workers > num_tiles) workers = (int)num_tiles;
   // every CTA must be resident at the same time (the channel halves wait on each other's flags)
-  kern<<<workers * C::NH, kE2Threads, C::SMEM, stream>>>(
-      map_e, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, tile_flags, epoch, flags, workers, g_edge_timing);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(workers * C::NH));
+  cfg.blockDim = dim3(kE2Threads);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C::MC ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  err = cudaLaunchKernelEx(&cfg, kern, map_e, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, tile_flags, epoch,
+                           flags, workers, g_edge_timing);
+  if (err != cudaSuccess) {
+    set_error("gnb_edge_forward_tc2: launch failed: %s", cudaGetErrorString(err));
+    return (int)err;
+  }
   return check_launch("gnb_edge_forward_tc2");
 }
 
