@@ -12,8 +12,8 @@
 //   e' written over it in place (same thread, same address)  ->  TMA store back to HBM.
 //   warp 0      : producer: TMA loads (lane 0) + the tile's (src, dst) indices into the stage's index area
 //   warp 1      : MMA issue (one lane)
-//   warps 2, 3  : TMA stores, one thread per epilogue group (wait for the group's epilogue, H = 256: for the other
-//                 channel half to have loaded the tile, store, release the stage)
+//   warps 2, 3  : TMA stores, one thread per two epilogue groups, polling (store the finished stage of whichever
+//                 group is ready, release the stage)
 //   warps 4..19 : epilogue, 4 groups x 4 TMEM lane quarters; group g takes tiles g, g+4, ... (one 32-edge chunk).
 //                 A thread owns ONE channel and walks its 32 consecutive edges: gathers of the (B1h, A2h) node
 //                 rows are coalesced across the warp, per-destination sums are register accumulators closed at
@@ -81,7 +81,9 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   using C = Edge2Cfg<H>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* bufs = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (an integer round-trip would demote every later
+  // access through these pointers to generic loads)
+  uint8_t* bufs = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   int* idx_area = reinterpret_cast<int*>(bufs + (size_t)C::NB * T::BUF_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(idx_area + C::NB * kE2IdxInts);
   uint64_t* full = bars;                    // [NB] producer (TMA bytes + 32 index lanes) -> MMA, epilogue
@@ -197,31 +199,42 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     }
   } else if (warp < kE2FirstEpiWarp) {
     // ---------------------------------------------------------------- TMA store of one epilogue group
-    // One store THREAD per epilogue group (lanes 0 and 16 of warps 2 and 3).  A group's phases of sfull are then
-    // consumed strictly in order by a thread that waits on nothing but that group, and since the producer loads
-    // tiles in order and NB <= 8, a group can never complete two phases ahead of its store thread (which would alias
-    // the phase parity and dead-lock) -- it could if two groups shared one store thread and one of them lagged.
-    if ((lane & 15) == 0) {
-      const int grp = (warp - 2) * 2 + (lane >> 4);
-      int i = 0;
-      for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
-        if (i % kE2Groups != grp) continue;
-        const int s = i % C::NB;
-        mbar_wait_sleep(&sfull[grp], (i / kE2Groups) & 1);
-        if (C::NH > 1 && !C::MC) {  // the other half must have read tile t before our channels of it are overwritten
-          while (ld_acquire2(tile_flags + t) < C::NH * epoch) __nanosleep(32);
-        }
-        const uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
+    // Lane 0 of warp 2 stores the tiles of groups 0 and 1, lane 0 of warp 3 those of groups 2 and 3.  It POLLS its
+    // two groups without blocking on either, so that each group's phases of sfull are consumed in order and
+    // promptly whatever the other group does (blocking on one group while the other runs two phases ahead would
+    // alias the phase parity and dead-lock; two lanes of one warp spinning on different barriers could starve
+    // each other).  Since the producer loads tiles in order and NB <= 8, a group is never two phases ahead.
+    if (lane == 0) {
+      const int g0 = (warp - 2) * 2;
+      int it[2] = {g0, g0 + 1};          // next tile iteration index of each of the two groups
+      auto remaining = [&](int k) { return worker + (int64_t)it[k] * workers < num_tiles; };
+      while (remaining(0) || remaining(1)) {
+        bool progressed = false;
 #pragma unroll
-        for (int kbl = 0; kbl < C::HC / kKB; ++kbl) {
-          const int kb = half * (C::HC / kKB) + kbl;
-          tma_store_2d(&map_e, stage + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
-          tma_store_2d(&map_e, stage + T::IMG_BYTES + kb * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT));
+        for (int k = 0; k < 2; ++k) {
+          if (!remaining(k)) continue;
+          const int i = it[k], grp = g0 + k;
+          if (!mbar_test(&sfull[grp], (i / kE2Groups) & 1)) continue;
+          const int64_t t = worker + (int64_t)i * workers;
+          const int s = i % C::NB;
+          if (C::NH > 1 && !C::MC) {  // the other half must have read tile t before our channels of it are overwritten
+            while (ld_acquire2(tile_flags + t) < C::NH * epoch) __nanosleep(32);
+          }
+          const uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
+#pragma unroll
+          for (int kbl = 0; kbl < C::HC / kKB; ++kbl) {
+            const int kb = half * (C::HC / kKB) + kbl;
+            tma_store_2d(&map_e, stage + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
+            tma_store_2d(&map_e, stage + T::IMG_BYTES + kb * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT));
+          }
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(&empty[s]);
+          if (C::MC) mbar_arrive_cluster(&empty[s], (uint32_t)(half ^ 1));   // the peer also writes into this stage
+          it[k] += kE2Groups;
+          progressed = true;
         }
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(&empty[s]);
-        if (C::MC) mbar_arrive_cluster(&empty[s], (uint32_t)(half ^ 1));   // the peer also writes into this stage
+        if (!progressed) __nanosleep(32);
       }
       tma_store_wait_all();
     }

@@ -35,7 +35,9 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
   using C = Lin2Cfg<K>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* bufs = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (an integer round-trip would demote every later
+  // access through these pointers to generic loads)
+  uint8_t* bufs = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bufs + (size_t)C::NB * T::BUF_BYTES);
   uint64_t* full = bars;             // [NB] TMA -> MMA
   uint64_t* empty = bars + C::NB;    // [NB] MMA -> TMA

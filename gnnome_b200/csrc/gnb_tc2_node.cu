@@ -14,7 +14,10 @@ namespace tc {
 constexpr int kEncR = 4;
 constexpr int kEncThreads = 256;
 
-template <int H>
+// HID = 16 (hidden_ne_features of every shipped configuration): the hidden layer of a row is computed ONCE, its 16
+// units spread over the H / 8 lanes that share the row, and broadcast by shuffle inside the fully unrolled j loop;
+// HID = 0: any hidden width, every lane recomputes the hidden units it needs.
+template <int H, int HID>
 __global__ void __launch_bounds__(kEncThreads)
 encode2_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx, int64_t rows, int in_f, int hid,
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2t,
@@ -55,6 +58,38 @@ encode2_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx, in
     for (int r = 0; r < kEncR; ++r)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[r][k] = bias[k];
+    if (HID > 0) {
+      constexpr int UPL = HID > 0 ? (HID + LPR - 1) / LPR : 1;   // hidden units per lane
+      const unsigned gmask = LPR >= 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (((threadIdx.x & 31) / LPR) * LPR));
+      float hv[kEncR][UPL];
+#pragma unroll
+      for (int r = 0; r < kEncR; ++r)
+#pragma unroll
+        for (int q = 0; q < UPL; ++q) {
+          const int j = lr + q * LPR;
+          float hsum = 0.f;
+          if (j < HID) {
+            hsum = bb1[j];
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+              if (f < in_f) hsum = fmaf(x[r][f], w1[j * in_f + f], hsum);
+            hsum = fmaxf(hsum, 0.f);
+          }
+          hv[r][q] = hsum;
+        }
+#pragma unroll
+      for (int j = 0; j < HID; ++j) {
+        const float4 wa = *reinterpret_cast<const float4*>(w2 + j * H + c0);
+        const float4 wb = *reinterpret_cast<const float4*>(w2 + j * H + c0 + 4);
+        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int r = 0; r < kEncR; ++r) {
+          const float hsum = __shfl_sync(gmask, hv[r][j / LPR], j % LPR, LPR < 32 ? LPR : 32);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[r][k] = fmaf(hsum, w[k], acc[r][k]);
+        }
+      }
+    } else
     for (int j = 0; j < hid; ++j) {
       const float4 wa = *reinterpret_cast<const float4*>(w2 + j * H + c0);
       const float4 wb = *reinterpret_cast<const float4*>(w2 + j * H + c0 + 4);
@@ -277,7 +312,8 @@ static int encode2_impl(const float* in, const int32_t* idx, int64_t rows, int i
                         const float* b1, const float* W2t, const float* b2, void* out16, float* out32,
                         cudaStream_t stream) {
   const size_t smem = ((size_t)hid * H + (size_t)hid * in_f + hid) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(encode2_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = hid == 16 ? encode2_kernel<H, 16> : encode2_kernel<H, 0>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("gnb_encode2: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     return (int)e;
@@ -285,7 +321,7 @@ static int encode2_impl(const float* in, const int32_t* idx, int64_t rows, int i
   constexpr int RPB = (kEncThreads / (H / 8)) * kEncR;
   const int64_t its = (rows + RPB - 1) / RPB;
   const int64_t cap = (int64_t)sm_count() * 4;
-  encode2_kernel<H><<<(unsigned)(its < cap ? its : cap), kEncThreads, smem, stream>>>(
+  kern<<<(unsigned)(its < cap ? its : cap), kEncThreads, smem, stream>>>(
       in, idx, rows, in_f, hid, W1, b1, W2t, b2, (__half*)out16, out32);
   return check_launch("gnb_encode2");
 }

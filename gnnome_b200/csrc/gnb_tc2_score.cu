@@ -36,7 +36,9 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
   using C = Score2Cfg<H, HS>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* bufs = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (an integer round-trip would demote every later
+  // access through these pointers to generic loads)
+  uint8_t* bufs = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   int* idx_area = reinterpret_cast<int*>(bufs + (size_t)C::NB * T::BUF_BYTES);
   float* t_s = reinterpret_cast<float*>(idx_area + C::NB * kS2IdxInts);   // [G][64][TS]
   float* w2t_s = t_s + C::T_FLOATS;                                       // [HS][32]  (W2 transposed)

@@ -2,6 +2,9 @@
 
 PyTorch is plumbing here: it owns the device memory and the stream; every byte of arithmetic
 happens in ``libgnnome_b200.so``."""
+import os
+import sys
+
 import torch
 
 from . import _lib
@@ -31,6 +34,9 @@ class LaunchLog:
         return {k: [a.elapsed_time(b) for a, b in v] for k, v in cls.events.items()}
 
 
+_TRACE = bool(os.environ.get('GNB_TRACE'))   # debugging: print every C-ABI call and synchronise after it
+
+
 class _logged:
     def __init__(self, name, device, launches=1):
         self.name, self.device, self.launches = name, device, launches
@@ -38,6 +44,8 @@ class _logged:
     def __enter__(self):
         self.dev_ctx = torch.cuda.device(self.device)
         self.dev_ctx.__enter__()
+        if _TRACE:
+            print(f'[gnb] {self.name} ...', file=sys.stderr, flush=True)
         if LaunchLog.enabled:
             LaunchLog.counts[self.name] = LaunchLog.counts.get(self.name, 0) + self.launches
             if LaunchLog.timing:
@@ -46,6 +54,9 @@ class _logged:
         return self
 
     def __exit__(self, *exc):
+        if _TRACE and exc[0] is None:
+            torch.cuda.synchronize(self.device)
+            print(f'[gnb] {self.name} done', file=sys.stderr, flush=True)
         if LaunchLog.enabled and LaunchLog.timing and exc[0] is None:
             end = torch.cuda.Event(enable_timing=True)
             end.record(torch.cuda.current_stream(self.device))
