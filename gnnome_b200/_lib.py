@@ -58,12 +58,22 @@ SIGNATURES = {
     'gnb_reverse_partial2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _L, _L, _P, _P]),
     'gnb_score_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'gnb_score_forward2': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'gnb_t_gather_add3': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _L, _P, _P, _P]),
+    'gnb_t_seg_sum': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _I, _P, _L, _P]),
+    'gnb_t_agg_fwd': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _I, _P, _P, _P]),
+    'gnb_t_agg_bwd_edge': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _P, _P, _P, _L, _I, _P, _I, _P]),
+    'gnb_t_agg_bwd_node': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _P, _P, _I, _P, _L, _P]),
+    'gnb_t_gate_fwd': (_I, [_P, _P, _L, _I, _P, _P, _P]),
+    'gnb_t_gate_bwd': (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P]),
+    'gnb_t_affine2': (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    'gnb_t_col_stats_workspace': (_S, [_L, _I]),
+    'gnb_t_col_stats': (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P]),
     'gnb_gather_rows': (_I, [_P, _P, _L, _I, _P, _P]),
     'gnb_gather_rows_ld': (_I, [_P, _L, _P, _L, _I, _P, _L, _P]),
     'gnb_scatter_rows': (_I, [_P, _P, _L, _I, _P, _P]),
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 

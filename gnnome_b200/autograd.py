@@ -1,0 +1,259 @@
+"""Training mode: the (Sym)GatedGCN layer, encoders and score predictor under torch autograd.
+
+``train.py`` of the reference runs ``model(g, x, e)`` in ``model.train()`` mode, takes a BCE / symmetry loss of the
+logits and calls ``loss.backward()`` (train.py:141-183, 329, 346).  The inference kernels are fused and keep no
+activations, so training has its own path: the layer is written as layers/gated_gcn_full.py:82-142 writes it, on top
+of a handful of graph primitives with hand-written CUDA forward and adjoint kernels (``csrc/gnb_train.cu``):
+
+  ``GatherAdd3``   apply_edges(u_add_v) + B_3(e)            z_p = B1h[src_p] + B2h[dst_p] + B3e_p
+  ``Agg``          update_all(u_mul_e, sum) / (copy_e, sum)  sum sigma*A[nbr] / (sum sigma + 1e-6), over in- or out-edges
+  ``Gate``         relu, residual, sigmoid                    e' = relu(ehat) + e, sigma = sigmoid(e')
+  ``BatchNormTrain``  BatchNorm1d with batch statistics over ALL E (or N) rows, running-stat update outside
+
+The dense ``nn.Linear`` products are plain library GEMMs (``F.linear``), torch's autograd engine chains the pieces.
+Edge rows are kept in dst-sorted position order; every sum runs over a CSR range in a fixed order (no atomics), so a
+training step is bit-reproducible.  fp32 throughout.  Only ``normalization='batch'`` is built.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .graph import GraphIndex, current_stream_ptr
+
+
+def _c(t):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise ValueError(f'expected a float32 CUDA tensor, got {t.dtype} on {t.device}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _call(name, device, *args):
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(getattr(lib, name)(*args, current_stream_ptr(device)), name)
+
+
+class GatherAdd3(torch.autograd.Function):
+    """z[p] = A[src_p] + B[dst_p] + C[p]; A, B node tables [N][W], C edge rows [E][W] (position order)."""
+
+    @staticmethod
+    def forward(ctx, gi: GraphIndex, A, B, C):
+        A, B, C = _c(A), _c(B), _c(C)
+        W = A.shape[1]
+        out = torch.empty((gi.E, W), dtype=torch.float32, device=A.device)
+        _call('gnb_t_gather_add3', A.device, gi.ref(), W, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+              C.data_ptr(), out.data_ptr())
+        ctx.gi, ctx.W = gi, W
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gi, W = ctx.gi, ctx.W
+        g = _c(g)
+        gA = torch.empty((gi.N, W), dtype=torch.float32, device=g.device)
+        gB = torch.empty_like(gA)
+        _call('gnb_t_seg_sum', g.device, gi.ref(), W, g.data_ptr(), 1, gA.data_ptr(), W)   # edges that leave the node
+        _call('gnb_t_seg_sum', g.device, gi.ref(), W, g.data_ptr(), 0, gB.data_ptr(), W)   # edges that enter the node
+        return None, gA, gB, g
+
+
+class Agg(torch.autograd.Function):
+    """out[i] = sum_p sigma[p] * A[nbr_p] / (sum_p sigma[p] + 1e-6).
+    mode 0: over the in-edges of i, nbr = src (gated_gcn_full.py:112-114); mode 1: out-edges, nbr = dst (:125-127)."""
+
+    @staticmethod
+    def forward(ctx, gi: GraphIndex, A, sigma, mode):
+        A, sigma = _c(A), _c(sigma)
+        W = A.shape[1]
+        den = torch.empty((gi.N, W), dtype=torch.float32, device=A.device)
+        out = torch.empty_like(den)
+        _call('gnb_t_agg_fwd', A.device, gi.ref(), W, A.data_ptr(), A.stride(0), sigma.data_ptr(), mode, den.data_ptr(),
+              out.data_ptr())
+        ctx.gi, ctx.W, ctx.mode = gi, W, mode
+        ctx.save_for_backward(A, sigma, den, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        gi, W, mode = ctx.gi, ctx.W, ctx.mode
+        A, sigma, den, out = ctx.saved_tensors
+        gout = _c(gout)
+        gsigma = torch.empty_like(sigma)
+        _call('gnb_t_agg_bwd_edge', gout.device, gi.ref(), W, gout.data_ptr(), out.data_ptr(), den.data_ptr(), A.data_ptr(),
+              A.stride(0), mode, gsigma.data_ptr(), 0)
+        gA = torch.empty_like(A)
+        _call('gnb_t_agg_bwd_node', gout.device, gi.ref(), W, gout.data_ptr(), den.data_ptr(), sigma.data_ptr(), mode,
+              gA.data_ptr(), W)
+        return None, gA, gsigma, None
+
+
+class Gate(torch.autograd.Function):
+    """e' = relu(ehat) (+ e_in), sigma = sigmoid(e')  (gated_gcn_full.py:107-111)."""
+
+    @staticmethod
+    def forward(ctx, ehat, e_in):
+        ehat = _c(ehat)
+        e_in = None if e_in is None else _c(e_in)
+        rows, W = ehat.shape
+        e_out, sigma = torch.empty_like(ehat), torch.empty_like(ehat)
+        _call('gnb_t_gate_fwd', ehat.device, ehat.data_ptr(), None if e_in is None else e_in.data_ptr(), rows, W,
+              e_out.data_ptr(), sigma.data_ptr())
+        ctx.has_res = e_in is not None
+        ctx.save_for_backward(ehat, sigma)
+        return e_out, sigma
+
+    @staticmethod
+    def backward(ctx, g_e, g_sigma):
+        ehat, sigma = ctx.saved_tensors
+        rows, W = ehat.shape
+        g_e = torch.zeros_like(ehat) if g_e is None else _c(g_e)
+        g_sigma = torch.zeros_like(ehat) if g_sigma is None else _c(g_sigma)
+        g_ehat = torch.empty_like(ehat)
+        g_ein = torch.empty_like(ehat) if ctx.has_res else None
+        _call('gnb_t_gate_bwd', ehat.device, g_e.data_ptr(), g_sigma.data_ptr(), ehat.data_ptr(), sigma.data_ptr(), rows, W,
+              g_ehat.data_ptr(), None if g_ein is None else g_ein.data_ptr())
+        return g_ehat, g_ein
+
+
+def _col_stats(a, b=None, shift_a=None, shift_b=None):
+    """fp64 [2][W]: column sums of a' = a - shift_a and of a' * b' (b None: a' * a'); deterministic (per-block fp32
+    partial sums, fp64 combine in block order)."""
+    lib = _lib.load()
+    rows, W = a.shape
+    out = torch.empty((2, W), dtype=torch.float64, device=a.device)
+    ws = torch.empty(max(lib.gnb_t_col_stats_workspace(rows, W), 8), dtype=torch.uint8, device=a.device)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    _call('gnb_t_col_stats', a.device, a.data_ptr(), ptr(b), ptr(shift_a), ptr(shift_b), rows, W, out.data_ptr(),
+          ws.data_ptr())
+    return out
+
+
+def _affine2(x, y, a, b, c):
+    rows, W = x.shape
+    out = torch.empty_like(x)
+    _call('gnb_t_affine2', x.device, x.data_ptr(), None if y is None else y.data_ptr(), a.data_ptr(),
+          None if b is None else b.data_ptr(), c.data_ptr(), rows, W, out.data_ptr())
+    return out
+
+
+class BatchNormTrain(torch.autograd.Function):
+    """nn.BatchNorm1d in training mode: statistics over all rows (biased variance for normalising).
+    Returns (y, batch_mean, batch_var_biased); the running-statistics update is the caller's (it is applied twice
+    per layer for ``bn_e``, gated_gcn_full.py:106,119)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = _c(x)
+        n = x.shape[0]
+        mean32 = (_col_stats(x)[0] / n).float().contiguous()          # pass 1: mean
+        st = _col_stats(x, shift_a=mean32)                             # pass 2: moments about it (no cancellation)
+        mean = mean32.double() + st[0] / n
+        var = (st[1] / n - (st[0] / n) ** 2).clamp_min_(0.0)
+        rstd = torch.rsqrt(var + eps)
+        a = weight.detach().double() * rstd
+        c = bias.detach().double() - mean * a
+        y = _affine2(x, None, a.float().contiguous(), None, c.float().contiguous())
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.n = n
+        mean_f, var_f = mean.float(), var.float()
+        ctx.mark_non_differentiable(mean_f, var_f)
+        return y, mean_f, var_f
+
+    @staticmethod
+    def backward(ctx, g, _gm, _gv):
+        x, weight, mean, rstd = ctx.saved_tensors
+        n = ctx.n
+        g = _c(g)
+        st = _col_stats(g, x, shift_b=mean.float().contiguous())       # sum g, sum g * (x - mean)
+        c1 = st[0]
+        c2 = rstd * st[1]                                               # sum g * xhat
+        w = weight.detach().double()
+        a = w * rstd
+        b = -w * rstd * rstd * c2 / n
+        c = -a * c1 / n - b * mean
+        gx = _affine2(g, x, a.float().contiguous(), b.float().contiguous(), c.float().contiguous())
+        return gx, c2.to(weight.dtype), c1.to(weight.dtype), None
+
+
+def batch_norm(bn: torch.nn.BatchNorm1d, x, training, updates=1):
+    """``bn(x)`` through the CUDA primitives; in training mode the running statistics are updated ``updates`` times
+    with the same batch statistics (unbiased variance, momentum), like calling the module ``updates`` times."""
+    if not training:
+        var = bn.running_var.detach().double()
+        a = bn.weight.double() / torch.sqrt(var + bn.eps)
+        c = bn.bias.double() - bn.running_mean.detach().double() * a
+        return x * a.float() + c.float()
+    y, mean, var = BatchNormTrain.apply(x, bn.weight, bn.bias, bn.eps)
+    if bn.track_running_stats:
+        n = x.shape[0]
+        with torch.no_grad():
+            unbiased = var * (n / max(n - 1, 1))
+            for _ in range(updates):
+                bn.num_batches_tracked += 1
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1 - m).add_(mean.to(bn.running_mean.dtype), alpha=m)
+                bn.running_var.mul_(1 - m).add_(unbiased.to(bn.running_var.dtype), alpha=m)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# layer / model forward in training mode
+# ------------------------------------------------------------------------------------------------
+def layer_forward(conv, gi: GraphIndex, h, e_pos):
+    """One (Sym)GatedGCN layer, edge rows in position order (gated_gcn_full.py:82-142 / :182-230)."""
+    if conv.normalization != 'batch':
+        raise NotImplementedError(f"training with normalization={conv.normalization!r} is not built")
+    sym = conv._symmetric
+    A1h, A2h = conv.A_1(h), conv.A_2(h)                                  # :91-92
+    B1h, B2h, B3e = conv.B_1(h), conv.B_2(h), conv.B_3(e_pos)            # :95-97
+    z = GatherAdd3.apply(gi, B1h, B2h, B3e)                              # :104-105
+    ehat = batch_norm(conv.bn_e, z, conv.training, updates=2 if sym else 1)   # :106 (+ :119 on the reversed graph)
+    e_new, sigma = Gate.apply(ehat, e_pos if conv.residual else None)    # :107-111
+    u = A1h + Agg.apply(gi, A2h, sigma, 0)                               # :112-114
+    if sym:
+        u = u + Agg.apply(gi, conv.A_3(h), sigma, 1)                     # :93, :125-127 (same sigma)
+    u = batch_norm(conv.bn_h, u, conv.training)                          # :131-132
+    h_new = torch.relu(u)                                                # :134
+    if conv.residual:
+        h_new = h_new + h                                                # :136-137
+    h_new = F.dropout(h_new, conv.dropout, training=conv.training)       # :139
+    return h_new, e_new
+
+
+def predictor_forward(pred, gi: GraphIndex, x, e_pos):
+    """ScorePredictor (score_predictor.py:12-24) with W1 split into its src / dst / edge column blocks."""
+    H = pred.in_features
+    W1, b1 = pred.W1.weight, pred.W1.bias
+    S1 = F.linear(x, W1[:, :H])
+    S2 = F.linear(x, W1[:, H:2 * H], b1)
+    E1 = F.linear(e_pos, W1[:, 2 * H:])
+    hid = torch.relu(GatherAdd3.apply(gi, S1, S2, E1))
+    return pred.W3(torch.relu(pred.W2(hid)))                             # [E][1], position order
+
+
+def model_forward(model, graph, x, e):
+    """``SymGatedGCNModel`` / ``GatedGCNModel(directed=True)`` forward under autograd (models/full_graph.py:22-30, 42-53)."""
+    gi = GraphIndex.from_graph(graph)
+    dev = gi.device
+    sym_model = hasattr(model, 'linear1_node')
+    if not sym_model and not getattr(model, 'directed', True):
+        raise NotImplementedError('training GatedGCNModel(directed=False) is not built')
+    for p in model.parameters():
+        if p.device != dev:
+            raise RuntimeError(f'training needs the model on {dev} (model.to(device)); found a parameter on {p.device}')
+    out_dev = x.device
+    x_d = x.to(device=dev, dtype=torch.float32)
+    order = gi.in_eid[:gi.E].long()
+    e_d = e.to(device=dev, dtype=torch.float32)[order]                   # edge rows in position order from here on
+    if sym_model:
+        h = model.linear2_node(torch.relu(model.linear1_node(x_d)))      # :26
+        ee = model.linear2_edge(torch.relu(model.linear1_edge(e_d)))     # :27
+    else:
+        ne, en = model.node_encoder, model.edge_encoder              # node_encoder.py:28-33, edge_encoder.py:27-32
+        h = ne.linear2(torch.relu(ne.linear1(x_d)))
+        ee = en.linear2(torch.relu(en.linear1(e_d)))
+    for conv in model.gnn.convs:                                         # processor.py:16-19
+        h, ee = layer_forward(conv, gi, h, ee)
+    s_pos = predictor_forward(model.predictor, gi, h, ee)
+    scores = torch.empty_like(s_pos).index_copy(0, order, s_pos)         # back to edge-id order
+    return scores.to(out_dev)

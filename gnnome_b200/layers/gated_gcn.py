@@ -206,6 +206,12 @@ class _GatedGCNBase(nn.Module):
         """``h, e = conv(g, h, e)`` with ``e`` in the graph's edge-id order (gated_gcn_full.py:82)."""
         gi = GraphIndex.from_graph(g)
         out_dev = h.device
+        if self.training:                      # under autograd (gnnome_b200.autograd), edge rows in position order inside
+            from ..autograd import layer_forward
+            order = gi.in_eid[:gi.E].long()
+            h_new, e_pos = layer_forward(self, gi, h.to(device=gi.device, dtype=torch.float32),
+                                         e.to(device=gi.device, dtype=torch.float32)[order])
+            return h_new.to(out_dev), torch.empty_like(e_pos).index_copy(0, order, e_pos).to(out_dev)
         h_d = h.detach().to(device=gi.device, dtype=torch.float32).contiguous()
         e_d = e.detach().to(device=gi.device, dtype=torch.float32).contiguous()
         if state_format(self.out_channels) == 'split16' and gi.E > 0:

@@ -2,6 +2,9 @@
 GatedGCNModel :33-53).  Same constructor signatures, sub-module names and ``state_dict`` keys;
 ``model(graph, x, e) -> (E, 1)`` fp32 logits in the graph's edge-id order, on the device of ``x``.
 
+In ``model.train()`` mode the forward runs under autograd through ``gnnome_b200.autograd`` (batch-statistics
+BatchNorm, hand-written forward / adjoint kernels for the graph primitives); what follows describes ``eval`` mode.
+
 Inputs may live on the CPU (the reference's ``inference.py:388`` forces ``device='cpu'``): they are
 moved to the current CUDA device, the graph is staged once (``GraphIndex``, cached on the graph
 object) and all edge state stays in dst-sorted position order until the scores are scattered back.
@@ -32,6 +35,9 @@ class SymGatedGCNModel(nn.Module):
         self.relu = nn.ReLU()
 
     def forward(self, graph, x, e):
+        if self.training:                      # train.py: under autograd, batch-statistics BatchNorm
+            from ..autograd import model_forward
+            return model_forward(self, graph, x, e)
         gi = GraphIndex.from_graph(graph)
         out_dev = x.device
         x_d, e_d = _to_dev(x, gi.device), _to_dev(e, gi.device)
@@ -57,6 +63,9 @@ class GatedGCNModel(nn.Module):
         self.predictor = layers.ScorePredictor(hidden_features, hidden_edge_scores)
 
     def forward(self, graph, x, e):
+        if self.training:
+            from ..autograd import model_forward
+            return model_forward(self, graph, x, e)
         gi = GraphIndex.from_graph(graph)
         out_dev = x.device
         x_d, e_d = _to_dev(x, gi.device), _to_dev(e, gi.device)

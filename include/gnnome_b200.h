@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 4
+#define GNB_ABI_VERSION 5
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -233,6 +233,42 @@ int gnb_score_forward_tc2(const gnb_graph_t* g, int H, int hs, const float* S, c
 int gnb_score_forward2(const gnb_graph_t* g, int H, int hs, const float* S, const float* W1e_t,
                        const float* W2, const float* b2, const float* W3, const float* b3,
                        const void* e16, float* scores, void* stream);
+
+/* ---- training-mode primitives (fp32 rows, edge rows in position order) ---------------------------------
+ * train.py runs the model under autograd (train.py:141-183,329,346).  gnnome_b200/autograd.py composes these graph
+ * primitives and their adjoints into the layer as layers/gated_gcn_full.py:82-142 does; nn.Linear products stay plain
+ * library GEMMs.  All sums walk CSR ranges in a fixed order (no atomics).  H % 4 == 0; tables may have a row pitch. */
+
+/* z[p] = A[in_src[p]] + B[in_dst[p]] (+ C[p])  -- apply_edges(u_add_v) + B_3(e), gated_gcn_full.py:104-105 */
+int gnb_t_gather_add3(const gnb_graph_t* g, int H, const float* A, int64_t ldA, const float* B, int64_t ldB,
+                      const float* C, float* out, void* stream);
+/* out[i] = sum of X[p] over the in-edges (mode 0) / out-edges (mode 1) of node i: adjoint of the gathers */
+int gnb_t_seg_sum(const gnb_graph_t* g, int H, const float* X, int mode, float* out, int64_t ldo, void* stream);
+/* out[i] = sum sigma[p] * A[nbr_p] / (den[i] + 1e-6), den[i] = sum sigma[p]; mode 0: in-edges, nbr = src
+ * (gated_gcn_full.py:112-114); mode 1: out-edges, nbr = dst (:125-127) */
+int gnb_t_agg_fwd(const gnb_graph_t* g, int H, const float* A, int64_t ldA, const float* sigma, int mode,
+                  float* den, float* out, void* stream);
+/* gsigma[p] (+)= gout[i_p] / (den[i_p] + 1e-6) * (A[nbr_p] - out[i_p]) */
+int gnb_t_agg_bwd_edge(const gnb_graph_t* g, int H, const float* gout, const float* out, const float* den,
+                       const float* A, int64_t ldA, int mode, float* gsigma, int accumulate, void* stream);
+/* gA[n] = sum over the edges whose neighbour end is n of gout[i_p] / (den[i_p] + 1e-6) * sigma[p] */
+int gnb_t_agg_bwd_node(const gnb_graph_t* g, int H, const float* gout, const float* den, const float* sigma,
+                       int mode, float* gA, int64_t ldg, void* stream);
+/* e' = relu(ehat) (+ e_in if not NULL), sigma = sigmoid(e')  -- gated_gcn_full.py:107-111 */
+int gnb_t_gate_fwd(const float* ehat, const float* e_in, int64_t rows, int H, float* e_out, float* sigma, void* stream);
+/* t = g_e + g_sigma * sigma * (1 - sigma); g_ehat = t * [ehat > 0]; g_ein = t (if not NULL) */
+int gnb_t_gate_bwd(const float* g_e, const float* g_sigma, const float* ehat, const float* sigma, int64_t rows,
+                   int H, float* g_ehat, float* g_ein, void* stream);
+/* out = a * x (+ b * y) + c with per-channel a, b, c: BatchNorm normalise (y NULL) and its input gradient */
+int gnb_t_affine2(const float* x, const float* y, const float* a, const float* b, const float* c, int64_t rows,
+                  int H, float* out, void* stream);
+/* With a' = a - shift_a and b' = b - shift_b per channel (NULL shifts = 0): out[0:H] = column sums of a',
+ * out[H:2H] = column sums of a' * b' (b NULL: a' * a'), in fp64, deterministic; workspace of
+ * gnb_t_col_stats_workspace(rows, H) bytes.  BatchNorm1d batch statistics over all E / N rows: mean from a first
+ * pass, variance about that mean from a second. */
+size_t gnb_t_col_stats_workspace(int64_t rows, int H);
+int gnb_t_col_stats(const float* a, const float* b, const float* shift_a, const float* shift_b, int64_t rows, int H,
+                    double* out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

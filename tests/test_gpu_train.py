@@ -1,0 +1,139 @@
+"""GPU parity of the training path (gnnome_b200.autograd): the graph primitives against torch reference autograd,
+and one full training step of the shipped model against the fixture produced by the reference's own code
+(oracle/make_golden.py: loss, every parameter gradient, BatchNorm buffers incl. the double bn_e update)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restatement as R
+from gnnome_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def gnb():
+    import gnnome_b200
+    from gnnome_b200 import _lib
+    _lib.load()
+    return gnnome_b200
+
+
+def _rand_graph(n, m, seed):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n - 3, (m,), generator=g)      # the last nodes stay isolated
+    dst = torch.randint(0, n - 3, (m,), generator=g)
+    return src.to(torch.int32), dst.to(torch.int32)
+
+
+def _seg(values, index, n):
+    return torch.zeros((n,) + tuple(values.shape[1:]), dtype=values.dtype, device=values.device).index_add_(0, index, values)
+
+
+@pytest.mark.parametrize('W', [4, 64, 100])
+def test_primitives_forward_and_adjoint(gnb, W):
+    from gnnome_b200 import autograd as ag
+    n, m = 50, 400
+    src, dst = _rand_graph(n, m, W)
+    gi = gnb.GraphIndex(src, dst, n)
+    ps, pd = gi.in_src[:m].long(), gi.in_dst[:m].long()        # endpoints in position order
+    torch.manual_seed(W)
+    A = torch.randn(n, W, device='cuda', dtype=torch.float64, requires_grad=True)
+    B = torch.randn(n, W, device='cuda', dtype=torch.float64, requires_grad=True)
+    C = torch.randn(m, W, device='cuda', dtype=torch.float64, requires_grad=True)
+    A32, B32, C32 = (t.detach().float().requires_grad_(True) for t in (A, B, C))
+    # ---- gather_add3 -> gate -> both aggregations, one scalar loss
+    def run(a, b, c, ours):
+        if ours:
+            z = ag.GatherAdd3.apply(gi, a, b, c)
+            e2, sg = ag.Gate.apply(z, c)
+            f = ag.Agg.apply(gi, a, sg, 0)
+            k = ag.Agg.apply(gi, b, sg, 1)
+        else:
+            z = a[ps] + b[pd] + c
+            e2 = torch.relu(z) + c
+            sg = torch.sigmoid(e2)
+            f = _seg(a[ps] * sg, pd, n) / (_seg(sg, pd, n) + 1e-6)
+            k = _seg(b[pd] * sg, ps, n) / (_seg(sg, ps, n) + 1e-6)
+        w = torch.linspace(0.5, 1.5, W, device='cuda', dtype=a.dtype)
+        return z, e2, f, k, ((f * w).sum() + (k * k).sum() * 0.1 + (e2 * w).sum() * 0.01)
+    zr, er, fr, kr, lr = run(A, B, C, False)
+    zo, eo, fo, ko, lo = run(A32, B32, C32, True)
+    for a, b in ((zo, zr), (eo, er), (fo, fr), (ko, kr)):
+        assert (a.double() - b).abs().max().item() < 2e-5
+    lr.backward()
+    lo.backward()
+    for a, b in ((A32, A), (B32, B), (C32, C)):
+        assert (a.grad.double() - b.grad).abs().max().item() < 1e-4 * max(1.0, b.grad.abs().max().item())
+
+
+def test_batchnorm_train_matches_torch(gnb):
+    from gnnome_b200 import autograd as ag
+    torch.manual_seed(0)
+    x = (torch.randn(5000, 64, device='cuda') * 3 + 1.5).requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    bn1, bn2 = torch.nn.BatchNorm1d(64).cuda(), torch.nn.BatchNorm1d(64).cuda()
+    with torch.no_grad():
+        bn1.weight.uniform_(0.5, 1.5); bn1.bias.normal_()
+        bn2.load_state_dict(bn1.state_dict())
+    w = torch.randn(5000, 64, device='cuda')
+    y1 = ag.batch_norm(bn1, x, True, updates=2)
+    (y1 * w).sum().backward()
+    bn2.train()
+    y2 = bn2(x2)
+    bn2(x2.detach())                                              # second call: running stats updated twice
+    (y2 * w).sum().backward()
+    assert (y1 - y2).abs().max().item() < 2e-5
+    assert (x.grad - x2.grad).abs().max().item() < 2e-4
+    assert (bn1.weight.grad - bn2.weight.grad).abs().max().item() < 2e-2 * bn2.weight.grad.abs().max().item() / 100 + 1e-2
+    assert (bn1.bias.grad - bn2.bias.grad).abs().max().item() < 1e-2
+    torch.testing.assert_close(bn1.running_mean, bn2.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bn1.running_var, bn2.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn1.num_batches_tracked) == 2
+
+
+def test_training_step_vs_reference_golden(gnb, golden, shipped_weights):
+    g = golden('sym_shipped_trainstep')
+    model = gnb.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch', dropout=None)
+    model.load_state_dict(shipped_weights, strict=True)
+    model.cuda().train()
+    logits = model((g['src'], g['dst'], g['num_nodes']), g['x'].cuda(), g['e'].cuda()).squeeze(-1)
+    loss = F.binary_cross_entropy_with_logits(logits, g['y'].cuda(), pos_weight=torch.tensor(g['pos_weight'], device='cuda'))
+    loss.backward()
+    assert (torch.sigmoid(logits.detach().cpu().double()) - torch.sigmoid(g['logits'].double())).abs().max().item() <= 1e-4
+    assert abs(loss.item() - g['loss'].item()) <= 1e-5 * max(1.0, abs(g['loss'].item()))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        ref = g['grads'][k]
+        assert p.grad is not None, k
+        err = (p.grad.cpu() - ref).abs().max().item()
+        scale = max(ref.abs().max().item(), 1e-6)
+        worst = max(worst, err / max(scale, 1e-3))
+        # biases that feed a train-mode BatchNorm have an exactly zero gradient: the reference holds rounding noise there
+        assert err <= 2e-3 * scale + 5e-6, f'{k}: grad err {err} (scale {scale})'
+    for k, b in model.named_buffers():
+        ref = g['buffers'][k]
+        if ref.dtype == torch.long:
+            assert int(b) == int(ref), k                       # bn_e: +2 per step, bn_h: +1
+        else:
+            torch.testing.assert_close(b.cpu(), ref, rtol=1e-4, atol=1e-5, msg=k)
+    print('worst relative gradient error', worst)
+
+
+def test_training_is_deterministic_and_eval_still_fused(gnb, shipped_weights):
+    src, dst = synth.make_assembly_graph(2000, 12000, seed=4)
+    x, e = synth.make_features(src, dst, 2000, seed=4)
+    src, dst, x, e = map(torch.from_numpy, (src, dst, x, e))
+    grads = []
+    for _ in range(2):
+        model = gnb.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch', dropout=None)
+        model.load_state_dict(shipped_weights, strict=True)
+        model.cuda().train()
+        out = model((src, dst, 2000), x.cuda(), e.cuda())
+        out.square().mean().backward()
+        grads.append(torch.cat([p.grad.flatten() for p in model.parameters()]))
+    assert torch.equal(grads[0], grads[1])                        # fixed summation order everywhere
+    model.eval()
+    with torch.no_grad():
+        ev = model((src, dst, 2000), x.cuda(), e.cuda())          # back on the fused inference kernels
+    assert ev.shape == (12000, 1) and torch.isfinite(ev).all()
