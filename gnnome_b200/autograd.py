@@ -12,7 +12,8 @@ of a handful of graph primitives with hand-written CUDA forward and adjoint kern
 
 The dense ``nn.Linear`` products are plain library GEMMs (``F.linear``), torch's autograd engine chains the pieces.
 Edge rows are kept in dst-sorted position order; every sum runs over a CSR range in a fixed order (no atomics), so a
-training step is bit-reproducible.  fp32 throughout.  Only ``normalization='batch'`` is built.
+training step is bit-reproducible.  fp32 throughout.  ``normalization='layer'`` models (nn.LayerNorm, row kernels
+of their own) run through this path in eval mode too: any hidden width that is a multiple of 4.
 """
 import torch
 import torch.nn.functional as F
@@ -175,6 +176,40 @@ class BatchNormTrain(torch.autograd.Function):
         return gx, c2.to(weight.dtype), c1.to(weight.dtype), None
 
 
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the channels of each row (normalization='layer', gated_gcn_full.py:39-42)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = _c(x)
+        rows, W = x.shape
+        y, xhat = torch.empty_like(x), torch.empty_like(x)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        w, b = _c(weight.detach()), _c(bias.detach())
+        _call('gnb_t_layer_norm_fwd', x.device, x.data_ptr(), w.data_ptr(), b.data_ptr(), rows, W, float(eps), y.data_ptr(),
+              xhat.data_ptr(), rstd.data_ptr())
+        ctx.save_for_backward(xhat, rstd, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xhat, rstd, w = ctx.saved_tensors
+        g = _c(g)
+        rows, W = g.shape
+        gx = torch.empty_like(g)
+        _call('gnb_t_layer_norm_bwd', g.device, g.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), w.data_ptr(), rows, W,
+              gx.data_ptr())
+        st = _col_stats(g, xhat)                       # sum g, sum g * xhat
+        return gx, st[1].to(w.dtype), st[0].to(w.dtype), None
+
+
+def normalize(norm, x, training, updates=1):
+    """``norm(x)`` for the layer's ``bn_h`` / ``bn_e`` sub-module: BatchNorm1d or LayerNorm."""
+    if isinstance(norm, torch.nn.LayerNorm):
+        return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+    return batch_norm(norm, x, training, updates)
+
+
 def batch_norm(bn: torch.nn.BatchNorm1d, x, training, updates=1):
     """``bn(x)`` through the CUDA primitives; in training mode the running statistics are updated ``updates`` times
     with the same batch statistics (unbiased variance, momentum), like calling the module ``updates`` times."""
@@ -201,18 +236,19 @@ def batch_norm(bn: torch.nn.BatchNorm1d, x, training, updates=1):
 # ------------------------------------------------------------------------------------------------
 def layer_forward(conv, gi: GraphIndex, h, e_pos):
     """One (Sym)GatedGCN layer, edge rows in position order (gated_gcn_full.py:82-142 / :182-230)."""
-    if conv.normalization != 'batch':
-        raise NotImplementedError(f"training with normalization={conv.normalization!r} is not built")
+    if conv.normalization not in ('batch', 'layer'):
+        raise NotImplementedError(f"normalization={conv.normalization!r} (the reference itself fails on 'none': bn_e is "
+                                  f"used unconditionally, gated_gcn_full.py:106)")
     sym = conv._symmetric
     A1h, A2h = conv.A_1(h), conv.A_2(h)                                  # :91-92
     B1h, B2h, B3e = conv.B_1(h), conv.B_2(h), conv.B_3(e_pos)            # :95-97
     z = GatherAdd3.apply(gi, B1h, B2h, B3e)                              # :104-105
-    ehat = batch_norm(conv.bn_e, z, conv.training, updates=2 if sym else 1)   # :106 (+ :119 on the reversed graph)
+    ehat = normalize(conv.bn_e, z, conv.training, updates=2 if sym else 1)    # :106 (+ :119 on the reversed graph)
     e_new, sigma = Gate.apply(ehat, e_pos if conv.residual else None)    # :107-111
     u = A1h + Agg.apply(gi, A2h, sigma, 0)                               # :112-114
     if sym:
         u = u + Agg.apply(gi, conv.A_3(h), sigma, 1)                     # :93, :125-127 (same sigma, SURVEY.md section 0)
-    u = batch_norm(conv.bn_h, u, conv.training)                          # :131-132
+    u = normalize(conv.bn_h, u, conv.training)                           # :131-132
     h_new = torch.relu(u)                                                # :134
     if conv.residual:
         h_new = h_new + h                                                # :136-137
@@ -231,6 +267,17 @@ def predictor_forward(pred, gi: GraphIndex, x, e_pos):
     return pred.W3(torch.relu(pred.W2(hid)))                             # [E][1], position order
 
 
+def _device_replica(model, dev):
+    """A copy of an eval-mode model on ``dev``, rebuilt when a parameter or buffer changes."""
+    key = tuple((id(t), t._version) for t in list(model.parameters()) + list(model.buffers())) + (str(dev),)
+    cache = model.__dict__.get('_gnb_replica')
+    if cache is None or cache[0] != key:
+        import copy
+        model.__dict__.pop('_gnb_replica', None)
+        cache = model.__dict__['_gnb_replica'] = (key, copy.deepcopy(model).to(dev).eval())
+    return cache[1]
+
+
 def model_forward(model, graph, x, e):
     """``SymGatedGCNModel`` / ``GatedGCNModel(directed=True)`` forward under autograd (models/full_graph.py:22-30, 42-53)."""
     gi = GraphIndex.from_graph(graph)
@@ -238,9 +285,10 @@ def model_forward(model, graph, x, e):
     sym_model = hasattr(model, 'linear1_node')
     if not sym_model and not getattr(model, 'directed', True):
         raise NotImplementedError('training GatedGCNModel(directed=False) is not built')
-    for p in model.parameters():
-        if p.device != dev:
-            raise RuntimeError(f'training needs the model on {dev} (model.to(device)); found a parameter on {p.device}')
+    if any(p.device != dev for p in model.parameters()):
+        if model.training:
+            raise RuntimeError(f'training needs the model on {dev}: call model.to(device) first')
+        model = _device_replica(model, dev)      # eval with CPU-resident parameters (inference.py:388)
     out_dev = x.device
     x_d = x.to(device=dev, dtype=torch.float32)
     order = gi.in_eid[:gi.E].long()

@@ -230,11 +230,83 @@ __global__ void col_stats_combine_kernel(const double* __restrict__ part, int64_
   out[H + c] = s2;
 }
 
+// LayerNorm over the channels of each row (nn.LayerNorm, gated_gcn_full.py:39-42): one warp per row.
+// fwd: xhat = (x - mean_row) * rstd_row, y = gamma * xhat + beta; saves xhat and rstd.
+__global__ void layer_norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int64_t rows, int W, float eps,
+                                      float* __restrict__ y, float* __restrict__ xhat, float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kT + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * kT) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + r * W;
+    float s = 0.f;
+    for (int c = lane; c < W; c += 32) s += xr[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)W;
+    float v = 0.f;
+    for (int c = lane; c < W; c += 32) {
+      const float d = xr[c] - mean;
+      v = fmaf(d, d, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rs = rsqrtf(v / (float)W + eps);
+    if (lane == 0) rstd[r] = rs;
+    for (int c = lane; c < W; c += 32) {
+      const float xh = (xr[c] - mean) * rs;
+      xhat[r * W + c] = xh;
+      y[r * W + c] = fmaf(gamma[c], xh, beta[c]);
+    }
+  }
+}
+
+// bwd: gxhat = g * gamma; gx = rstd * (gxhat - mean_row(gxhat) - xhat * mean_row(gxhat * xhat))
+__global__ void layer_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xhat,
+                                      const float* __restrict__ rstd, const float* __restrict__ gamma, int64_t rows,
+                                      int W, float* __restrict__ gx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * kT + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * kT) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < W; c += 32) {
+      const float gh = g[r * W + c] * gamma[c];
+      s1 += gh;
+      s2 = fmaf(gh, xhat[r * W + c], s2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / (float)W, m2 = s2 / (float)W, rs = rstd[r];
+    for (int c = lane; c < W; c += 32) gx[r * W + c] = rs * (g[r * W + c] * gamma[c] - m1 - xhat[r * W + c] * m2);
+  }
+}
+
 }  // namespace train
 }  // namespace gnb
 
 using namespace gnb;
 using namespace gnb::train;
+
+extern "C" int gnb_t_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int W, float eps,
+                                    float* y, float* xhat, float* rstd, void* stream) {
+  GNB_REQUIRE(W > 0, "gnb_t_layer_norm_fwd: bad width %d", W);
+  if (rows == 0) return 0;
+  GNB_REQUIRE(x && gamma && beta && y && xhat && rstd, "null pointer");
+  layer_norm_fwd_kernel<<<blocks_for(rows * 32), kT, 0, (cudaStream_t)stream>>>(x, gamma, beta, rows, W, eps, y, xhat, rstd);
+  return check_launch("gnb_t_layer_norm_fwd");
+}
+
+extern "C" int gnb_t_layer_norm_bwd(const float* g, const float* xhat, const float* rstd, const float* gamma, int64_t rows,
+                                    int W, float* gx, void* stream) {
+  GNB_REQUIRE(W > 0, "gnb_t_layer_norm_bwd: bad width %d", W);
+  if (rows == 0) return 0;
+  GNB_REQUIRE(g && xhat && rstd && gamma && gx, "null pointer");
+  layer_norm_bwd_kernel<<<blocks_for(rows * 32), kT, 0, (cudaStream_t)stream>>>(g, xhat, rstd, gamma, rows, W, gx);
+  return check_launch("gnb_t_layer_norm_bwd");
+}
 
 static int check_train_graph(const gnb_graph_t* g, int H) {
   GNB_REQUIRE(g != nullptr && g->in_ptr && g->out_ptr, "graph not staged");

@@ -128,7 +128,7 @@ class _GatedGCNBase(nn.Module):
         """One layer with edge rows already in dst-sorted position order.  ``e_pos`` is updated IN
         PLACE (legal: e'_p depends only on e_p, h[src_p], h[dst_p]) and returned."""
         if self.training:
-            raise NotImplementedError('training mode runs through gnnome_b200.autograd (not built yet)')
+            raise NotImplementedError('training mode runs through gnnome_b200.autograd: call forward()')
         if self.in_channels != self.out_channels:
             raise NotImplementedError('in_channels != out_channels is not supported by the CUDA path')
         H = self.out_channels
@@ -168,7 +168,7 @@ class _GatedGCNBase(nn.Module):
         """One layer on the split16 path: ``h32`` fp32 rows (residual), ``h16`` / ``e16`` split fp16 images
         (the tensor-core operands).  ``e16`` is updated IN PLACE; returns ``(h32', h16', e16)``."""
         if self.training:
-            raise NotImplementedError('training mode runs through gnnome_b200.autograd (not built yet)')
+            raise NotImplementedError('training mode runs through gnnome_b200.autograd: call forward()')
         if self.in_channels != self.out_channels:
             raise NotImplementedError('in_channels != out_channels is not supported by the CUDA path')
         H = self.out_channels
@@ -206,10 +206,17 @@ class _GatedGCNBase(nn.Module):
         """``h, e = conv(g, h, e)`` with ``e`` in the graph's edge-id order (gated_gcn_full.py:82)."""
         gi = GraphIndex.from_graph(g)
         out_dev = h.device
-        if self.training:                      # under autograd (gnnome_b200.autograd), edge rows in position order inside
+        if self.training or self.normalization == 'layer' or self.in_channels != self.out_channels:
+            # gnnome_b200.autograd primitives (any width that is a multiple of 4), position order inside
             from ..autograd import layer_forward
             order = gi.in_eid[:gi.E].long()
-            h_new, e_pos = layer_forward(self, gi, h.to(device=gi.device, dtype=torch.float32),
+            conv = self
+            if any(p.device != gi.device for p in self.parameters()):
+                if self.training:
+                    raise RuntimeError(f'training needs the layer on {gi.device}: call .to(device) first')
+                from ..autograd import _device_replica
+                conv = _device_replica(self, gi.device)
+            h_new, e_pos = layer_forward(conv, gi, h.to(device=gi.device, dtype=torch.float32),
                                          e.to(device=gi.device, dtype=torch.float32)[order])
             return h_new.to(out_dev), torch.empty_like(e_pos).index_copy(0, order, e_pos).to(out_dev)
         h_d = h.detach().to(device=gi.device, dtype=torch.float32).contiguous()

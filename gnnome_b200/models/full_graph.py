@@ -35,7 +35,8 @@ class SymGatedGCNModel(nn.Module):
         self.relu = nn.ReLU()
 
     def forward(self, graph, x, e):
-        if self.training:                      # train.py: under autograd, batch-statistics BatchNorm
+        if self.training or self.gnn.convs[0].normalization == 'layer':
+            # train.py: under autograd, batch-statistics BatchNorm; LayerNorm models run on the same primitives
             from ..autograd import model_forward
             return model_forward(self, graph, x, e)
         gi = GraphIndex.from_graph(graph)
@@ -63,7 +64,7 @@ class GatedGCNModel(nn.Module):
         self.predictor = layers.ScorePredictor(hidden_features, hidden_edge_scores)
 
     def forward(self, graph, x, e):
-        if self.training:
+        if self.directed and (self.training or self.gnn.convs[0].normalization == 'layer'):
             from ..autograd import model_forward
             return model_forward(self, graph, x, e)
         gi = GraphIndex.from_graph(graph)

@@ -262,6 +262,14 @@ int gnb_t_gate_bwd(const float* g_e, const float* g_sigma, const float* ehat, co
 /* out = a * x (+ b * y) + c with per-channel a, b, c: BatchNorm normalise (y NULL) and its input gradient */
 int gnb_t_affine2(const float* x, const float* y, const float* a, const float* b, const float* c, int64_t rows,
                   int H, float* out, void* stream);
+/* nn.LayerNorm over the W channels of each row (gated_gcn_full.py:39-42): y = gamma * xhat + beta with
+ * xhat = (x - mean_row) / sqrt(var_row + eps) (biased variance); xhat [rows][W] and rstd [rows] are kept for the backward */
+int gnb_t_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int W, float eps,
+                         float* y, float* xhat, float* rstd, void* stream);
+/* gx = rstd * (g*gamma - mean_row(g*gamma) - xhat * mean_row(g*gamma*xhat)); d gamma / d beta are the column sums of
+ * g * xhat and g (gnb_t_col_stats(g, xhat)) */
+int gnb_t_layer_norm_bwd(const float* g, const float* xhat, const float* rstd, const float* gamma, int64_t rows, int W,
+                         float* gx, void* stream);
 /* With a' = a - shift_a and b' = b - shift_b per channel (NULL shifts = 0): out[0:H] = column sums of a',
  * out[H:2H] = column sums of a' * b' (b NULL: a' * a'), in fp64, deterministic; workspace of
  * gnb_t_col_stats_workspace(rows, H) bytes.  BatchNorm1d batch statistics over all E / N rows: mean from a first

@@ -137,3 +137,72 @@ def test_training_is_deterministic_and_eval_still_fused(gnb, shipped_weights):
     with torch.no_grad():
         ev = model((src, dst, 2000), x.cuda(), e.cuda())          # back on the fused inference kernels
     assert ev.shape == (12000, 1) and torch.isfinite(ev).all()
+
+
+def test_layer_norm_matches_torch(gnb):
+    from gnnome_b200 import autograd as ag
+    torch.manual_seed(1)
+    for W in (32, 100, 256):
+        x = (torch.randn(777, W, device='cuda') * 2 + 0.5).requires_grad_(True)
+        x2 = x.detach().clone().requires_grad_(True)
+        ln1, ln2 = torch.nn.LayerNorm(W).cuda(), torch.nn.LayerNorm(W).cuda()
+        with torch.no_grad():
+            ln1.weight.uniform_(0.5, 1.5); ln1.bias.normal_()
+            ln2.load_state_dict(ln1.state_dict())
+        w = torch.randn(777, W, device='cuda')
+        y1 = ag.normalize(ln1, x, True)
+        (y1 * w).sum().backward()
+        y2 = ln2(x2)
+        (y2 * w).sum().backward()
+        assert (y1 - y2).abs().max().item() < 2e-5
+        assert (x.grad - x2.grad).abs().max().item() < 1e-4
+        assert (ln1.weight.grad - ln2.weight.grad).abs().max().item() < 1e-3
+        assert (ln1.bias.grad - ln2.bias.grad).abs().max().item() < 1e-3
+
+
+def test_layernorm_model_vs_reference_golden(gnb, golden):
+    """normalization='layer' (reference fixture sym_layernorm, H=32) through the primitive path, CPU-resident model."""
+    g = golden('sym_layernorm')
+    model = gnb.models.SymGatedGCNModel(2, 2, 32, 16, 3, 64, 'layer')
+    model.load_state_dict(g['state_dict'], strict=True)
+    model.eval()
+    with torch.no_grad():
+        out = model((g['src'], g['dst'], g['num_nodes']), g['x'], g['e'])
+    assert out.shape == g['logits'].shape and out.device.type == 'cpu'
+    assert (torch.sigmoid(out.double()) - torch.sigmoid(g['logits'].double())).abs().max().item() <= 1e-4
+    assert (out - g['logits']).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize('kind,norm', [('gated', 'batch'), ('sym', 'layer')])
+def test_training_step_vs_oracle_autograd(gnb, kind, norm):
+    """Other model families: loss and gradients against the oracle restatement differentiated by torch on the CPU."""
+    n, m, H, L = 400, 2400, 32, 2
+    src, dst = synth.make_assembly_graph(n, m, seed=11)
+    x, e = synth.make_features(src, dst, n, seed=11)
+    src, dst, x, e = map(torch.from_numpy, (src, dst, x, e))
+    y = (torch.rand(m, generator=torch.Generator().manual_seed(2)) < 0.7).float()
+    torch.manual_seed(5)
+    if kind == 'sym':
+        model = gnb.models.SymGatedGCNModel(2, 2, H, 16, L, 64, norm, dropout=None)
+    else:
+        model = gnb.models.GatedGCNModel(2, 2, H, 16, L, 64, norm, dropout=None, directed=True)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in sd.items()}
+    ref = R.model_forward(p, src, dst, n, x, e, model=kind, normalization=norm, training=True, cast=False).squeeze(-1)
+    ref_loss = F.binary_cross_entropy_with_logits(ref, y)
+    ref_loss.backward()
+    model.cuda().train()
+    out = model((src, dst, n), x.cuda(), e.cuda()).squeeze(-1)
+    loss = F.binary_cross_entropy_with_logits(out, y.cuda())
+    loss.backward()
+    assert (out.detach().cpu() - ref.detach()).abs().max().item() <= 2e-4
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5
+    for k, prm in model.named_parameters():
+        rg = p[k].grad
+        err = (prm.grad.cpu() - rg).abs().max().item()
+        assert err <= 2e-3 * max(rg.abs().max().item(), 1e-6) + 5e-6, f'{k}: {err}'
+    for k, b in model.named_buffers():
+        if b.dtype == torch.long:
+            assert int(b) == int(p[k]), k
+        else:
+            torch.testing.assert_close(b.cpu(), p[k].detach(), rtol=1e-4, atol=1e-5, msg=k)
