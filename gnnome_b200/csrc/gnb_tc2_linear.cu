@@ -28,7 +28,11 @@ struct Lin2Cfg {
   static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
-template <int K>
+// kMC: two neighbouring channel blocks of a worker form a 2-CTA cluster; each CTA issues half of the X tile's TMA boxes
+// with .multicast::cluster (rank 0 the hi halves, rank 1 the lo halves), so a tile is pulled out of L2 once per pair
+// instead of once per channel block -- the kernel is bound by that L2 -> SM traffic (X is re-read by all 5H / 128
+// channel blocks).  A stage is written by both CTAs, so its `empty` barrier collects the MMA commits of both.
+template <int K, bool kMC>
 __global__ void __launch_bounds__(kLin2Threads, 1)
 node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, const __half* __restrict__ Wp, const float* __restrict__ bias, int M,
                        float* __restrict__ out, int64_t ld_out, int nblk, int workers) {
@@ -46,13 +50,14 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
 
   const int cb = blockIdx.x % nblk, worker = blockIdx.x / nblk;
+  const int rank = kMC ? (int)(blockIdx.x & 1) : 0;   // position in the cluster (nblk is even when kMC)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t num_tiles = (rows + kLin2NT - 1) / kLin2NT;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::NB; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], kMC ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&dfull[i], 1);
@@ -63,7 +68,8 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (kMC) cluster_sync_all();   // the peer's multicast must find initialised barriers
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp >= kLin2FirstEpiWarp && warp < kLin2FirstEpiWarp + 4)
@@ -83,8 +89,13 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
         for (int kb = 0; kb < T::KBLOCKS; ++kb) {
-          tma_load_2d(stage + kb * T::KB_BYTES, &map_x, kb * kKB, (int)(t * kLin2NT), &full[s]);
-          tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_x, K + kb * kKB, (int)(t * kLin2NT), &full[s]);
+          if (kMC) {
+            tma_load_2d_mc(stage + rank * T::IMG_BYTES + kb * T::KB_BYTES, &map_x, rank * K + kb * kKB, (int)(t * kLin2NT),
+                           &full[s], (uint16_t)3);
+          } else {
+            tma_load_2d(stage + kb * T::KB_BYTES, &map_x, kb * kKB, (int)(t * kLin2NT), &full[s]);
+            tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_x, K + kb * kKB, (int)(t * kLin2NT), &full[s]);
+          }
         }
       }
       __syncwarp();
@@ -100,7 +111,8 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
       if (elect_one()) {
         issue_tile_mma_sw128<K, kLin2NT>(tmem_base, tmem_base + C::D_COL0 + d * kLin2NT,
                                          smem_u32(bufs + (size_t)s * T::BUF_BYTES));
-        mma_commit(&empty[s]);
+        if (kMC) mma_commit_mc(&empty[s], (uint16_t)3);   // both CTAs of the pair write into each other's stage
+        else mma_commit(&empty[s]);
         mma_commit(&dfull[d]);
       }
       __syncwarp();
@@ -145,7 +157,8 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kMC) cluster_sync_all();   // the peer may still multicast into this CTA's stages / arrive on its barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
@@ -153,8 +166,10 @@ template <int K>
 static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, const float* bias, int M, float* out,
                                 int64_t ld_out, cudaStream_t stream) {
   using C = Lin2Cfg<K>;
-  cudaError_t e = cudaFuncSetAttribute(node_linear_tc2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)C::SMEM);
+  const int nblk_ = (M + kM - 1) / kM;
+  const bool mc = nblk_ % 2 == 0;
+  auto kern = mc ? node_linear_tc2_kernel<K, true> : node_linear_tc2_kernel<K, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) {
     set_error("gnb_node_linear_tc2: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(e));
     return (int)e;
@@ -168,8 +183,23 @@ static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, c
   const int64_t num_tiles = (rows + kLin2NT - 1) / kLin2NT;
   int workers = sms / nblk;
   if (workers > num_tiles) workers = (int)num_tiles;
-  node_linear_tc2_kernel<K><<<workers * nblk, kLin2Threads, C::SMEM, stream>>>(map_x, rows, (const __half*)Wp,
-                                                                              bias, M, out, ld_out, nblk, workers);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(workers * nblk));
+  cfg.blockDim = dim3(kLin2Threads);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = mc ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, map_x, rows, (const __half*)Wp, bias, M, out, ld_out, nblk, workers);
+  if (e != cudaSuccess) {
+    set_error("gnb_node_linear_tc2: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
   return check_launch("gnb_node_linear_tc2");
 }
 
