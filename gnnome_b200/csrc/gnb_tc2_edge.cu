@@ -28,7 +28,8 @@ namespace tc {
 
 constexpr int kE2NT = 32;        // edges per tile (MMA N) = edges per epilogue warp = carry granularity
 constexpr int kE2Chunk = kE2NT;
-constexpr int kE2Groups = 4;     // epilogue groups of four warps (one per TMEM lane quarter); group g takes tiles g, g+4, ...
+constexpr int kE2Groups = 4;     // epilogue groups of four warps (one per TMEM lane quarter); group g takes tiles g, g+G, ...
+                                 // (five groups were measured slower: the schedulers are issue-bound, r01h)
 constexpr int kE2DBufs = 8;      // accumulator buffers (two per group: the MMA of a group's next tile overlaps its epilogue)
 constexpr int kE2FirstEpiWarp = 4;
 constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 4 * kE2Groups);
@@ -205,13 +206,23 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     // alias the phase parity and dead-lock; two lanes of one warp spinning on different barriers could starve
     // each other).  Since the producer loads tiles in order and NB <= 8, a group is never two phases ahead.
     if (lane == 0) {
-      const int g0 = (warp - 2) * 2;
-      int it[2] = {g0, g0 + 1};          // next tile iteration index of each of the two groups
-      auto remaining = [&](int k) { return worker + (int64_t)it[k] * workers < num_tiles; };
-      while (remaining(0) || remaining(1)) {
+      constexpr int kFirst = (kE2Groups + 1) / 2;          // warp 2 serves groups [0, kFirst), warp 3 the rest
+      const int g0 = (warp == 2) ? 0 : kFirst;
+      const int ng = (warp == 2) ? kFirst : kE2Groups - kFirst;
+      int it[kFirst];                                      // next tile iteration index of each served group
+#pragma unroll
+      for (int k = 0; k < kFirst; ++k) it[k] = g0 + k;
+      auto remaining = [&](int k) { return k < ng && worker + (int64_t)it[k] * workers < num_tiles; };
+      auto any_remaining = [&]() {
+        bool r = false;
+#pragma unroll
+        for (int k = 0; k < kFirst; ++k) r = r || remaining(k);
+        return r;
+      };
+      while (any_remaining()) {
         bool progressed = false;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < kFirst; ++k) {
           if (!remaining(k)) continue;
           const int i = it[k], grp = g0 + k;
           if (!mbar_test(&sfull[grp], (i / kE2Groups) & 1)) continue;
