@@ -43,6 +43,8 @@ WORKLOADS = {
     'small': (100_000, 600_000, 256, 8, 'synthetic 100k nodes / 600k edges, hidden=256, L=8 (debug size)'),
 }
 CPU_SAMPLE = (40_000, 240_000)      # bounded sample of the workload for the CPU arm (same H, L, generator)
+if os.environ.get('GNB_BENCH_CPU_SAMPLE'):   # tests shrink it
+    CPU_SAMPLE = tuple(int(v) for v in os.environ['GNB_BENCH_CPU_SAMPLE'].split(','))
 HIDDEN_NE, HIDDEN_SCORES = 16, 64   # configs/hyperparameters.py:24-25 of the reference
 
 
