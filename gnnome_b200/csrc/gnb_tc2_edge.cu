@@ -129,7 +129,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     auto load_idx = [&](int64_t t, int (&r)[3]) {
       const int64_t p0 = t * kE2NT + lane;
       r[0] = (p0 < E) ? g.in_src[p0] : 0;
-      r[1] = (p0 < E) ? g.in_dst[p0] : -1;
+      r[1] = (p0 < E) ? g.in_dst[p0] : 0;    // rows past a ragged end: any valid node (every use is guarded by n)
       r[2] = -1;
       if (lane == 0 && t > 0) r[2] = g.in_dst[t * kE2NT - 1];
       if (lane == 1 && (t + 1) * kE2NT < E) r[2] = g.in_dst[(t + 1) * kE2NT];
@@ -140,7 +140,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     auto prefetch_rows = [&](const int (&r)[3]) {
       {
         const int sj = r[0], dj = r[1];
-        if (dj >= 0) {
+        {   // rows past a ragged end carry node 0: a harmless prefetch
           const char* a = reinterpret_cast<const char*>(P + (int64_t)sj * ldP + 2 * half * C::HC);
 #pragma unroll
           for (int l = 0; l < C::HC * 8 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
@@ -330,9 +330,19 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         *reinterpret_cast<int4*>(&dj[0]) = *reinterpret_cast<const int4*>(ia_dst + b * kEB);
         *reinterpret_cast<int4*>(&dj[4]) = *reinterpret_cast<const int4*>(ia_dst + b * kEB + 4);
 #pragma unroll
-        for (int u = 0; u < kEB; ++u) {
-          xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj[u] * ldPb));
-          xb[u] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)max(dj[u], 0) * ldPb));   // -1: past a ragged end
+        for (int u = 0; u < kEB; ++u) xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj[u] * ldPb));
+        // B2h[dst]: the four edges of a quad share it unless a destination segment opens at its 2nd..4th edge
+        const unsigned m8 = segmask >> (b * kEB);
+#pragma unroll
+        for (int hq = 0; hq < kEB; hq += 4) {
+          if (((m8 >> hq) & 0xeu) == 0) {   // warp-uniform
+            const float v = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj[hq] * ldPb));
+            xb[hq] = v; xb[hq + 1] = v; xb[hq + 2] = v; xb[hq + 3] = v;
+          } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              xb[hq + w] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj[hq + w] * ldPb));
+          }
         }
       };
       // Stage address of row r of the chunk for this thread's channel: st_hi + r * 128 + (((c%64)/8 ^ r%8) << 4).
