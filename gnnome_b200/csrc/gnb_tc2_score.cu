@@ -94,11 +94,26 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
       r[4] = (p0 < E) ? g.in_eid[p0] : -1;
       r[5] = (p1 < E) ? g.in_eid[p1] : -1;
     };
+    // The projected node rows S[src][0:hs], S[dst][hs:2hs] are gathered by the epilogue; whoever touches a row
+    // first would wait for HBM, so the producer pulls them into L2 a tile or two ahead (it has the endpoints).
+    auto prefetch_rows = [&](const int (&r)[6]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const char* a = reinterpret_cast<const char*>(S + (int64_t)r[k] * 2 * HS);
+        const char* b = reinterpret_cast<const char*>(S + (int64_t)r[2 + k] * 2 * HS + HS);
+#pragma unroll
+        for (int l = 0; l < HS * 4 / 128; ++l) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(b + l * 128));
+        }
+      }
+    };
     int cur[6], nxt[6];
     if (worker < num_tiles) load_idx(worker, cur);
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
+      prefetch_rows(cur);
       mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
       if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;

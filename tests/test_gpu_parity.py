@@ -294,3 +294,21 @@ def test_empty_and_degenerate_graphs(gnb, backend, shipped_weights):
         out = model((s, s, 1), x, e)
         ref = R.model_forward(shipped_weights, s, s, 1, x, e)
     assert _prob_err(out, ref) <= PROB_TOL
+
+
+def test_full_size_properties_cfg2(gnb):
+    """BASELINE config 2 (1M nodes / 6M edges, H=128, L=8) is too big for the oracle: size-independent properties
+    instead -- bit-reproducible, finite, and equivariant under a relabelling of the edges."""
+    n, m, H, L = 1_000_000, 6_000_000, 128, 8
+    src, dst, n, x, e = _graph(n, m, seed=0)
+    torch.manual_seed(0)
+    model = gnb.models.SymGatedGCNModel(2, 2, H, 16, L, 64, 'batch').cuda().eval()
+    xd, ed = x.cuda(), e.cuda()
+    with torch.no_grad():
+        gi = gnb.GraphIndex(src, dst, n)
+        a = model(gi, xd, ed)
+        b = model(gi, xd, ed)
+        assert torch.equal(a, b) and torch.isfinite(a).all() and a.shape == (m, 1)
+        perm = torch.randperm(m, generator=torch.Generator().manual_seed(1))
+        c = model((src[perm], dst[perm], n), xd, ed[perm.cuda()])
+    assert _prob_err(a[perm.cuda()], c) <= PROB_TOL
