@@ -73,9 +73,12 @@ SIGNATURES = {
     'gnb_gather_rows': (_I, [_P, _P, _L, _I, _P, _P]),
     'gnb_gather_rows_ld': (_I, [_P, _L, _P, _L, _I, _P, _L, _P]),
     'gnb_scatter_rows': (_I, [_P, _P, _L, _I, _P, _P]),
+    'gnb_degree_rows': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _P]),
+    'gnb_zscore_workspace': (_S, []),
+    'gnb_zscore_cols': (_I, [_P, _L, _I, _I, _P, _P, _P]),
 }
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 

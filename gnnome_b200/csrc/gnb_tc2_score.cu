@@ -3,7 +3,7 @@
 // with S[n] = [x_n W1s^T | x_n W1d^T + b1] projected once per node (gnb_node_linear_tc2).  Per 64-edge tile:
 //   e . W1e^T          tcgen05 (W1e, zero-padded to 128 rows, resident in TMEM; e tile by TMA, fp16 hi/lo split)
 //   phase A (epilogue) thread = hidden unit k: t[edge][k] = relu(D[k][edge] + S[src][k] + S[dst][hs + k]) -> smem
-//   phase B            4 threads per edge: u = relu(W2 t + b2), score = W3 . u + b3 -> scores[in_eid[p]]
+//   phase B            lane = unit m, 8 edges per warp: u = relu(W2 t + b2), score = W3 . u + b3 -> scores[in_eid[p]]
 //   warp 0 : producer (TMA + src/dst/eid of the tile)   warp 1 : MMA issue   warps 4..19 : two epilogue groups
 #include "gnb_tma.cuh"
 
@@ -20,7 +20,7 @@ template <int H, int HS>
 struct Score2Cfg {
   using T = Tile2<H, kS2NT>;
   static constexpr int NB = (H >= 256) ? 2 : 4;
-  static constexpr int TS = HS + 1;                      // padded stride of the hidden tile
+  static constexpr int TS = HS + 4;                      // stride of the hidden tile: rows stay 16-byte aligned
   static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + kS2Groups * kS2NT);
   static constexpr uint32_t D_COL0 = 2 * T::W_COLS;
   static constexpr size_t T_FLOATS = (size_t)kS2Groups * kS2NT * TS;
@@ -156,7 +156,8 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
     // ---------------------------------------------------------------- epilogue
     const int ew = warp - kS2FirstEpiWarp;
     const int grp = ew >> 3, sub = (ew >> 2) & 1, q = warp & 3;
-    const int gt = threadIdx.x - 32 * (kS2FirstEpiWarp + 8 * grp);   // thread index inside the group (0..255)
+    const int w8 = ew & 7;                    // warp inside the group: phase B takes edges [8 * w8, 8 * w8 + 8)
+    const int my_edge = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // see the butterfly below
     const int k = q * 32 + lane;              // hidden unit (TMEM lane)
     const bool unit_ok = k < HS;              // warp-uniform
     const float bias3 = b3[0];
@@ -171,7 +172,7 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
       // copy what phase A / B need out of the stage's index area, then release our share of the stage
       const int my_src = ia[sub * 32 + lane];
       const int my_dst = ia[kS2NT + sub * 32 + lane];
-      const int b_eid = ia[2 * kS2NT + (gt >> 2)];
+      const int b_eid = ia[2 * kS2NT + w8 * 8 + my_edge];
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
       mbar_wait_sleep(&dfull[grp], (i / kS2Groups) & 1, 32);
@@ -200,27 +201,57 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
       __syncwarp();
       if (lane == 0) mbar_arrive(&dempty[grp]);
       named_bar_sync(1 + grp, 256);
-      // ---- phase B: 4 threads per edge, 8 of the 32 second-layer units each -------------------------------
+      // ---- phase B: lane = second-layer unit m, each warp takes 8 of the tile's 64 edges ------------------------
+      // The W2 row of the unit sits in registers (32 columns at a time) and the hidden tile is read with 16-byte
+      // broadcast loads: 24 shared-memory wavefronts per edge instead of 72 with four threads per edge.
       {
-        const int edge = gt >> 2, part = gt & 3;
-        float u8[8];
+        const float* trow = tg + (size_t)(w8 * 8) * C::TS;
+        float acc[8];
+        const float bias2 = b2_s[lane];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) u8[m] = b2_s[part * 8 + m];
-        const float* trow = tg + edge * C::TS;
-#pragma unroll 4
-        for (int kk = 0; kk < HS; ++kk) {
-          const float tv = trow[kk];
-          const float4 wa = *reinterpret_cast<const float4*>(w2t_s + kk * 32 + part * 8);
-          const float4 wb = *reinterpret_cast<const float4*>(w2t_s + kk * 32 + part * 8 + 4);
-          u8[0] = fmaf(wa.x, tv, u8[0]); u8[1] = fmaf(wa.y, tv, u8[1]); u8[2] = fmaf(wa.z, tv, u8[2]); u8[3] = fmaf(wa.w, tv, u8[3]);
-          u8[4] = fmaf(wb.x, tv, u8[4]); u8[5] = fmaf(wb.y, tv, u8[5]); u8[6] = fmaf(wb.z, tv, u8[6]); u8[7] = fmaf(wb.w, tv, u8[7]);
+        for (int ed = 0; ed < 8; ++ed) acc[ed] = bias2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HS; c0 += 32) {
+          float w[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = w2t_s[(c0 + j) * 32 + lane];
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            float4 tv[8];
+#pragma unroll
+            for (int ed = 0; ed < 8; ++ed) tv[ed] = *reinterpret_cast<const float4*>(trow + ed * C::TS + c0 + k4 * 4);
+#pragma unroll
+            for (int ed = 0; ed < 8; ++ed) acc[ed] = fmaf(w[k4 * 4 + 0], tv[ed].x, acc[ed]);
+#pragma unroll
+            for (int ed = 0; ed < 8; ++ed) acc[ed] = fmaf(w[k4 * 4 + 1], tv[ed].y, acc[ed]);
+#pragma unroll
+            for (int ed = 0; ed < 8; ++ed) acc[ed] = fmaf(w[k4 * 4 + 2], tv[ed].z, acc[ed]);
+#pragma unroll
+            for (int ed = 0; ed < 8; ++ed) acc[ed] = fmaf(w[k4 * 4 + 3], tv[ed].w, acc[ed]);
+          }
         }
-        float part_sum = 0.f;
+        // score = W3 . relu(u) + b3: sum over the 32 lanes for 8 edges at once (transposed butterfly, 9 shuffles);
+        // afterwards lane 4 * j holds edge j of this warp
+        const float w3v = w3_s[lane];
+        float v[8];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) part_sum = fmaf(w3_s[part * 8 + m], fmaxf(u8[m], 0.f), part_sum);
-        part_sum += __shfl_xor_sync(kFull, part_sum, 1);
-        part_sum += __shfl_xor_sync(kFull, part_sum, 2);
-        if (part == 0 && b_eid >= 0) scores[b_eid] = part_sum + bias3;
+        for (int ed = 0; ed < 8; ++ed) v[ed] = w3v * fmaxf(acc[ed], 0.f);
+        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+        float r4[4], r2[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float keep = h16 ? v[j + 4] : v[j], send = h16 ? v[j] : v[j + 4];
+          r4[j] = keep + __shfl_xor_sync(kFull, send, 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float keep = h8 ? r4[j + 2] : r4[j], send = h8 ? r4[j] : r4[j + 2];
+          r2[j] = keep + __shfl_xor_sync(kFull, send, 8);
+        }
+        float r1 = (h4 ? r2[1] : r2[0]) + __shfl_xor_sync(kFull, h4 ? r2[0] : r2[1], 4);
+        r1 += __shfl_xor_sync(kFull, r1, 2);
+        r1 += __shfl_xor_sync(kFull, r1, 1);
+        if ((lane & 3) == 0 && b_eid >= 0) scores[b_eid] = r1 + bias3;
       }
       named_bar_sync(1 + grp, 256);   // t_s of this group is free again
     }

@@ -312,3 +312,27 @@ def score_forward_tc2(gi: GraphIndex, H, hs, S, Wp, W2, b2, W3, b3, e16, scores)
                                              _f32(b2, 'b2'), _f32(W3, 'W3'), _f32(b3, 'b3'), _img(e16, 'e16'),
                                              _f32(scores, 'scores'), current_stream_ptr(e16.device)),
                    'gnb_score_forward_tc2')
+
+
+def degree_rows(gi, swap=False):
+    """(N, 2) float32: ``(in_degree, out_degree)`` of every node, ``(out, in)`` with ``swap`` (train.py:117-118)."""
+    lib = _lib.load()
+    x = torch.empty((gi.N, 2), dtype=torch.float32, device=gi.device)
+    with _logged('gnb_degree_rows', gi.device):
+        _lib.check(lib.gnb_degree_rows(gi.ref(), int(bool(swap)), x.data_ptr(), current_stream_ptr(gi.device)),
+                   'gnb_degree_rows')
+    return x
+
+
+def zscore_cols(x, col_mask, want_stats=False):
+    """In place ``x[:, c] = (x[:, c] - mean) / std`` (unbiased std) for the columns in ``col_mask`` (bit c)."""
+    lib = _lib.load()
+    if x.ndim != 2 or not 1 <= x.shape[1] <= 4:
+        raise ValueError('x must be (rows, 1..4)')
+    rows, cols = x.shape
+    ws = torch.empty(lib.gnb_zscore_workspace() // 8, dtype=torch.float64, device=x.device)
+    stats = torch.empty((cols, 2), dtype=torch.float64, device=x.device) if want_stats else None
+    with _logged('gnb_zscore_cols', x.device, launches=3):
+        _lib.check(lib.gnb_zscore_cols(_f32(x, 'x'), rows, cols, int(col_mask), _opt(stats), ws.data_ptr(),
+                                       current_stream_ptr(x.device)), 'gnb_zscore_cols')
+    return (x, stats) if want_stats else x

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 5
+#define GNB_ABI_VERSION 6
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -277,6 +277,20 @@ int gnb_t_layer_norm_bwd(const float* g, const float* xhat, const float* rstd, c
 size_t gnb_t_col_stats_workspace(int64_t rows, int H);
 int gnb_t_col_stats(const float* a, const float* b, const float* shift_a, const float* shift_b, int64_t rows, int H,
                     double* out, void* workspace, void* stream);
+
+/* ---- input features of the scoring pass (the callers' host-side torch code, moved to the device) ---------------------
+ * x[i] = (in_degree(i), out_degree(i)) as floats -- g.in_degrees() / g.out_degrees() of utils/data_utils.py:50-51 --
+ * in the column order of inference.py:420 / train.py:120; swap != 0 gives (out, in), the order train.py:117-118 uses for
+ * the reversed graph.  x is [N][2], 8-byte aligned. */
+int gnb_degree_rows(const gnb_graph_t* g, int swap, float* x, void* stream);
+/* In place on x [rows][cols] (cols <= 4), for every column c whose bit is set in col_mask:
+ *   x[r][c] = (x[r][c] - mean_c) / std_c,  std unbiased (rows - 1)
+ * i.e. torch's (v - v.mean()) / v.std() of inference.py:416-419, train.py:113-116 and utils/data_utils.py:36.  Mean and
+ * variance (about the mean, second pass) are accumulated in fp64 in a fixed order; the normalisation itself is fp32 like
+ * the reference's.  stats (device, may be NULL) receives double[cols][2] = (mean, std).  A constant column gives nan
+ * (0 / 0), one row gives nan, as in the reference.  workspace: gnb_zscore_workspace() bytes, 8-byte aligned. */
+size_t gnb_zscore_workspace(void);
+int gnb_zscore_cols(float* x, int64_t rows, int cols, int col_mask, double* stats, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,3 +44,25 @@ def quiet():
     """``models/full_graph.py:25`` prints ``x.shape`` on every forward."""
     with contextlib.redirect_stdout(io.StringIO()):
         yield
+
+
+def load_functions(relpath, names, namespace):
+    """Execute the *unmodified* source of the named top-level functions of a reference file in ``namespace``.
+
+    For reference modules that cannot be imported whole here (``train.py`` needs ``dgl.data`` and ``wandb`` runs,
+    ``utils/data_utils.py`` needs Biopython): the functions' own code still runs, only the module-level imports are
+    replaced by what the caller puts in ``namespace`` (torch, F, the dgl shim, ``get_hyperparameters`` ...)."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    source = open(path).read()
+    tree = ast.parse(source, filename=path)
+    found = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, 'exec')
+            exec(code, namespace)
+            found[node.name] = namespace[node.name]
+    missing = set(names) - set(found)
+    if missing:
+        raise RuntimeError(f'{relpath}: no top-level function(s) {sorted(missing)}')
+    return found

@@ -214,3 +214,33 @@ def init_state_dict(model='sym', node_features=2, edge_features=2, hidden=64, hi
     linear('predictor.W2', hidden_edge_scores, 32)
     linear('predictor.W3', 32, 1)
     return sd
+
+
+# ---- the callers' code either side of model(g, x, e) ---------------------------------
+
+def zscore(v):
+    """``(v - v.mean()) / v.std()`` with torch's unbiased std (utils/data_utils.py:36, train.py:113-116)."""
+    return (v - v.mean()) / v.std()
+
+
+def edge_input_features(overlap_length, overlap_similarity, use_similarities=True):
+    """utils/data_utils.py:31-41 (``preprocess_graph``): e = [z(overlap_length.float()), overlap_similarity]."""
+    ol_len = zscore(overlap_length.float())
+    if not use_similarities:
+        return ol_len.unsqueeze(-1)
+    return torch.cat((ol_len.unsqueeze(-1), overlap_similarity.unsqueeze(-1)), dim=1)
+
+
+def node_input_features(src, dst, n, reverse=False):
+    """utils/data_utils.py:50-51 (float in/out degrees) + train.py:112-120 / inference.py:413-420 (z-score, concatenate;
+    ``reverse`` swaps the columns: train.py:117-118)."""
+    in_deg = torch.bincount(dst.long(), minlength=n).float().unsqueeze(1)
+    out_deg = torch.bincount(src.long(), minlength=n).float().unsqueeze(1)
+    pe_in, pe_out = zscore(in_deg), zscore(out_deg)
+    return torch.cat((pe_out, pe_in) if reverse else (pe_in, pe_out), dim=1)
+
+
+def symmetry_loss(org_scores, rev_scores, labels, pos_weight, alpha):
+    """train.py:103-109."""
+    bce = lambda s: F.binary_cross_entropy_with_logits(s, labels, pos_weight=pos_weight, reduction='none')  # noqa: E731
+    return (bce(org_scores) + bce(rev_scores) + alpha * torch.abs(org_scores - rev_scores)).mean()
