@@ -77,10 +77,13 @@ def main():
         mt = models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch', dropout=None)
         mt.load_state_dict(sd, strict=True)
         mt.train()
+        seen = []   # every forward's output: [org] for BCE, [org, rev] for the symmetry loss
+        hook = mt.register_forward_hook(lambda mod, inp, out: seen.append(out.detach().squeeze(-1).clone()))
         with rr.quiet():
             loss, logits = ns[fn](g, mt, *args)
+        hook.remove()
         loss.backward()
-        rec[name] = dict(loss=loss.detach(), logits=logits.detach(),
+        rec[name] = dict(loss=loss.detach(), logits=logits.detach(), forwards=seen,
                          grads={k: p.grad.clone() for k, p in mt.named_parameters()},
                          buffers={k: b.clone() for k, b in mt.named_buffers()})
         print(name, 'loss', float(loss))

@@ -126,12 +126,30 @@ def test_training_losses_vs_reference_functions(gnb, golden, shipped_weights, ki
     model.load_state_dict(shipped_weights, strict=True)
     model.cuda().train()
     pw = torch.tensor([g['pos_weight']], device='cuda')
+    ref = g[kind]
+    seen = []
+    hook = model.register_forward_hook(lambda mod, inp, out: seen.append(out.squeeze(-1)))
     if kind == 'bce':
         loss, logits = A.get_bce_loss_full(ag, model, pw)
+        loss.backward()
     else:
         loss, logits = A.get_symmetry_loss_full(ag, model, pw, g['alpha'])
-    loss.backward()
-    ref = g[kind]
+        # |org - rev| has a kink where the two forwards agree to fp32 noise (28 of the 3600 edges are within 1e-4, the
+        # closest at 2e-6): there the reference's sign(org - rev) is a coin toss, and one flipped edge moves the first
+        # layers' gradients by more than the tolerance.  Compare gradients for the reference's choice of subgradient.
+        org, rev = seen
+        ref_org, ref_rev = (t.cuda() for t in ref['forwards'])
+        assert (torch.sigmoid(rev.detach().double()) - torch.sigmoid(ref_rev.double())).abs().max().item() <= 1e-4
+        sign_ref = torch.sign(ref_org - ref_rev)
+        flips = int((torch.sign(org.detach() - rev.detach()) != sign_ref).sum())
+        print('edges whose sign(org - rev) differs from the reference:', flips)
+        assert flips <= 8
+        y = ag.edata['y'].cuda()
+        bce = lambda s: torch.nn.functional.binary_cross_entropy_with_logits(s, y, pos_weight=pw, reduction='none')  # noqa: E731
+        pinned = (bce(org) + bce(rev) + g['alpha'] * (org - rev) * sign_ref).mean()
+        assert abs(pinned.item() - loss.item()) <= 1e-6
+        pinned.backward()
+    hook.remove()
     assert logits.shape == ref['logits'].shape
     assert (torch.sigmoid(logits.detach().cpu().double()) - torch.sigmoid(ref['logits'].double())).abs().max().item() <= 1e-4
     assert abs(loss.item() - ref['loss'].item()) <= 1e-5 * max(1.0, abs(ref['loss'].item()))
@@ -147,9 +165,9 @@ def test_training_losses_vs_reference_functions(gnb, golden, shipped_weights, ki
         else:
             torch.testing.assert_close(b.cpu(), r, rtol=1e-4, atol=1e-5, msg=k)
     if kind == 'sym':                             # the reversed graph is staged once and reused
-        rev = ag._gnb_reversed
+        g_rev = ag._gnb_reversed
         A.get_symmetry_loss_full(ag, model, pw, g['alpha'])
-        assert ag._gnb_reversed is rev and rev._gnb_index_cache is not None
+        assert ag._gnb_reversed is g_rev and g_rev._gnb_index_cache is not None
 
 
 def test_dataset_directory_like_graph_dataset(gnb, golden, tmp_path):
