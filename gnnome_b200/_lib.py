@@ -76,9 +76,12 @@ SIGNATURES = {
     'gnb_degree_rows': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _P]),
     'gnb_zscore_workspace': (_S, []),
     'gnb_zscore_cols': (_I, [_P, _L, _I, _I, _P, _P, _P]),
+    'gnb_subgraph_workspace': (_I, [_L, _L, ctypes.POINTER(_S)]),
+    'gnb_subgraph_count': (_I, [_P, _P, _P, _L, _L, _P, _S, _P, _P]),
+    'gnb_subgraph_fill': (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P]),
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 

@@ -10,7 +10,10 @@ The reference keeps an assembly graph as a DGLGraph written with ``dgl.save_grap
 * ``preprocess_graph`` / ``add_positional_encoding`` / ``get_full_ne_features`` -- same names and results as the
   reference's, but the degrees come from the staged ``GraphIndex`` and the z-scores from ``gnb_zscore_cols`` on the GPU;
 * ``compute_scores`` -- the ``get scores`` block of ``inference()``; writes ``{idx}_predicts.pt`` like the reference;
-* ``symmetry_loss`` / ``get_bce_loss_full`` / ``get_symmetry_loss_full`` -- the full-graph losses of train.py.
+* ``symmetry_loss`` / ``get_bce_loss_full`` / ``get_symmetry_loss_full`` -- the full-graph losses of train.py;
+* ``node_subgraph`` / ``mask_graph_strandwise`` and the ``*_partition`` feature / loss functions -- the reference's
+  strand-wise masking and mini-batch code (train.py:91-100, 125-135, 148-155, 173-185) on device-built induced subgraphs
+  (section 8(f) row 3; METIS itself is not built: any node set works).
 
 Everything that touches N- or E-sized data runs on the CUDA device (there is no CPU fallback); the losses are the caller's
 own torch code in the reference and stay torch here (4 bytes per edge)."""
@@ -137,6 +140,64 @@ def compute_scores(model, g, idx=0, inference_dir=None, device=None):
         os.makedirs(inference_dir, exist_ok=True)
         torch.save(scores, path)
     return scores
+
+
+def node_subgraph(g, keep, device=None):
+    """``dgl.node_subgraph(g, keep, store_ids=True)`` (train.py:95): the subgraph induced by the nodes with ``keep`` set,
+    renumbered in increasing id order, edges in the order of their ids; every ``ndata`` / ``edata`` entry is sliced and
+    ``ndata['_ID']`` / ``edata['_ID']`` map back to ``g``.  All of it on the device (``gnb_subgraph_*``)."""
+    gi = GraphIndex.from_graph(g, device)
+    node_id, edge_id, sub_src, sub_dst = ops.node_subgraph(keep, gi.src, gi.dst, gi.N)
+    nid, eid = node_id.long(), edge_id.long()
+    sub = AssemblyGraph(sub_src, sub_dst, int(node_id.numel()),
+                        {k: v.to(gi.device)[eid] for k, v in g.edata.items() if k != '_ID'},
+                        {k: v.to(gi.device)[nid] for k, v in g.ndata.items() if k != '_ID'})
+    sub.ndata['_ID'], sub.edata['_ID'] = node_id, edge_id
+    return sub
+
+
+def mask_graph_strandwise(g, fraction, device=None, generator=None):
+    """train.py:91-100: keep each strand pair (nodes 2k, 2k+1) with probability ``fraction`` and take the induced
+    subgraph.  The random draw is made on the device, as in the reference when it trains on a GPU."""
+    device = _cuda_device(device)
+    keep_half = torch.rand(g.num_nodes() // 2, device=device, generator=generator) < fraction
+    keep = torch.zeros(g.num_nodes(), dtype=torch.bool, device=device)   # an unpaired last node is dropped
+    keep[0:2 * keep_half.numel():2] = keep_half
+    keep[1:2 * keep_half.numel():2] = keep_half
+    return node_subgraph(g, keep, device)
+
+
+def get_partition_ne_features(sub_g, g, reverse=False, device=None):
+    """train.py:125-135: features of a mini-batch ``sub_g`` of ``g``: the parent's degrees at ``sub_g.ndata['_ID']``,
+    z-scored within the batch, and the parent's ``e`` rows at ``sub_g.edata['_ID']``."""
+    device = _cuda_device(device)
+    if 'in_deg' not in g.ndata or 'out_deg' not in g.ndata:
+        add_positional_encoding(g, device)
+    if 'e' not in g.edata:
+        preprocess_graph(g, device=device)
+    nid, eid = sub_g.ndata['_ID'].to(device).long(), sub_g.edata['_ID'].to(device).long()
+    cols = ('out_deg', 'in_deg') if reverse else ('in_deg', 'out_deg')
+    x = torch.stack([g.ndata[c].to(device=device, dtype=torch.float32)[nid] for c in cols], dim=1).contiguous()
+    return ops.zscore_cols(x, 0b11), g.edata['e'].to(device)[eid]
+
+
+def get_bce_loss_partition(sub_g, g, model, pos_weight, device=None):
+    """train.py:148-155 -> (loss, logits) of one mini-batch."""
+    x, e = get_partition_ne_features(sub_g, g, reverse=False, device=device)
+    logits = model(sub_g, x, e).squeeze(-1)
+    labels = g.edata['y'].to(logits.device)[sub_g.edata['_ID'].to(logits.device).long()].to(logits.dtype)
+    return F.binary_cross_entropy_with_logits(logits, labels, pos_weight=_pos_weight(pos_weight, logits)), logits
+
+
+def get_symmetry_loss_partition(sub_g, g, model, pos_weight, alpha, device=None):
+    """train.py:173-185: the symmetry loss of one mini-batch (second forward over the reversed batch)."""
+    x, e = get_partition_ne_features(sub_g, g, reverse=False, device=device)
+    logits_org = model(sub_g, x, e).squeeze(-1)
+    labels = g.edata['y'].to(logits_org.device)[sub_g.edata['_ID'].to(logits_org.device).long()].to(logits_org.dtype)
+    sub_rev = sub_g.reversed()
+    x, e = get_partition_ne_features(sub_rev, g, reverse=True, device=device)
+    logits_rev = model(sub_rev, x, e).squeeze(-1)
+    return symmetry_loss(logits_org, logits_rev, labels, pos_weight, alpha=alpha), logits_org
 
 
 def _pos_weight(pos_weight, like):

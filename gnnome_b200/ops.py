@@ -336,3 +336,34 @@ def zscore_cols(x, col_mask, want_stats=False):
         _lib.check(lib.gnb_zscore_cols(_f32(x, 'x'), rows, cols, int(col_mask), _opt(stats), ws.data_ptr(),
                                        current_stream_ptr(x.device)), 'gnb_zscore_cols')
     return (x, stats) if want_stats else x
+
+
+def node_subgraph(keep, src, dst, num_nodes):
+    """``dgl.node_subgraph(g, keep, store_ids=True)`` on index tensors: ``keep`` (N,) bool / uint8, ``src`` / ``dst`` the
+    parent's int32 edge list (CUDA).  Returns ``(node_id, edge_id, sub_src, sub_dst)``, all int32: the two '_ID' maps and
+    the renumbered endpoints.  One host read of the two sizes sits between the two kernel passes."""
+    import ctypes
+    lib = _lib.load()
+    device = src.device
+    if not src.is_cuda or src.dtype != torch.int32 or dst.dtype != torch.int32 or not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError('src / dst must be contiguous int32 CUDA tensors')
+    keep = keep.to(device=device).ne(0).to(torch.uint8).contiguous()
+    N, E = int(num_nodes), int(src.numel())
+    if keep.numel() != N:
+        raise ValueError(f'keep has {keep.numel()} entries for {N} nodes')
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(lib.gnb_subgraph_workspace(N, E, ctypes.byref(nbytes)), 'gnb_subgraph_workspace')
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+    counts = torch.empty(2, dtype=torch.int64, device=device)
+    with _logged('gnb_subgraph_count', device, launches=5):
+        _lib.check(lib.gnb_subgraph_count(keep.data_ptr(), src.data_ptr(), dst.data_ptr(), N, E, ws.data_ptr(),
+                                          nbytes.value, counts.data_ptr(), current_stream_ptr(device)), 'gnb_subgraph_count')
+    n_sub, e_sub = (int(v) for v in counts.tolist())     # the one synchronisation: output sizes
+    i32 = dict(dtype=torch.int32, device=device)
+    node_id, edge_id = torch.empty(n_sub, **i32), torch.empty(e_sub, **i32)
+    sub_src, sub_dst = torch.empty(e_sub, **i32), torch.empty(e_sub, **i32)
+    with _logged('gnb_subgraph_fill', device, launches=2):
+        _lib.check(lib.gnb_subgraph_fill(keep.data_ptr(), src.data_ptr(), dst.data_ptr(), N, E, ws.data_ptr(),
+                                         node_id.data_ptr(), edge_id.data_ptr(), sub_src.data_ptr(), sub_dst.data_ptr(),
+                                         current_stream_ptr(device)), 'gnb_subgraph_fill')
+    return node_id, edge_id, sub_src, sub_dst

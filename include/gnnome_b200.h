@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 6
+#define GNB_ABI_VERSION 7
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -291,6 +291,23 @@ int gnb_degree_rows(const gnb_graph_t* g, int swap, float* x, void* stream);
  * (0 / 0), one row gives nan, as in the reference.  workspace: gnb_zscore_workspace() bytes, 8-byte aligned. */
 size_t gnb_zscore_workspace(void);
 int gnb_zscore_cols(float* x, int64_t rows, int cols, int col_mask, double* stats, void* workspace, void* stream);
+
+/* ---- node-induced subgraph: dgl.node_subgraph(g, keep, store_ids=True) (train.py:91-100 strand-wise masking; the
+ * '_ID' maps the mini-batch code reads, train.py:125-135) --------------------------------------------------------------
+ * keep [N] bytes (non-zero = kept); src / dst the parent's edge list in edge-id order.  Kept nodes are renumbered in
+ * increasing order of their id; an edge is induced when both endpoints are kept, and induced edges keep the order of
+ * their ids.  Two passes sharing one workspace of gnb_subgraph_workspace bytes (256-byte aligned):
+ *   gnb_subgraph_count  counts[0] = kept nodes, counts[1] = induced edges (device int64[2]); the caller reads them to
+ *                       size the outputs
+ *   gnb_subgraph_fill   node_id [n'] / edge_id [e'] = the '_ID' maps, sub_src / sub_dst [e'] = renumbered endpoints
+ *                       (an output may be NULL when its count is 0)
+ * keep must be 4-byte, src / dst 16-byte aligned. */
+int gnb_subgraph_workspace(int64_t num_nodes, int64_t num_edges, size_t* bytes);
+int gnb_subgraph_count(const uint8_t* keep, const int32_t* src, const int32_t* dst, int64_t num_nodes,
+                       int64_t num_edges, void* workspace, size_t workspace_bytes, int64_t* counts, void* stream);
+int gnb_subgraph_fill(const uint8_t* keep, const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges,
+                      void* workspace, int32_t* node_id, int32_t* edge_id, int32_t* sub_src, int32_t* sub_dst,
+                      void* stream);
 
 #ifdef __cplusplus
 }

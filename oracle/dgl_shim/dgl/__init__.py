@@ -144,3 +144,26 @@ def add_self_loop(g):
 
 def seed(_):  # dgl.seed, used by the reference's utils.set_seed
     return None
+
+
+NID, EID = '_ID', '_ID'   # dgl.NID / dgl.EID: the feature names store_ids writes
+
+
+def node_subgraph(g, nodes, relabel_nodes=True, store_ids=True):
+    """DGL 0.8 ``dgl.node_subgraph``: the subgraph induced by ``nodes`` (a bool mask over the nodes or a tensor of ids).
+    Nodes are relabelled in the order given (increasing ids for a mask), an edge is kept when both endpoints are, kept
+    edges stay in the order of their ids (DGL doc example: edges 0..4 of a 5-cycle, nodes [0, 1, 4] -> EID [0, 4]);
+    every node / edge feature is sliced, and ``store_ids`` adds the original ids as ``ndata['_ID']`` / ``edata['_ID']``."""
+    assert relabel_nodes, 'only the relabelling form is used by the reference'
+    nodes = torch.as_tensor(nodes)
+    ids = torch.nonzero(nodes, as_tuple=False).flatten() if nodes.dtype == torch.bool else nodes.long()
+    new_id = torch.full((g._n,), -1, dtype=torch.long)
+    new_id[ids] = torch.arange(ids.numel())
+    s, d = g._src.long(), g._dst.long()
+    eids = torch.nonzero((new_id[s] >= 0) & (new_id[d] >= 0), as_tuple=False).flatten()
+    sub = DGLGraph(new_id[s[eids]].to(g._src.dtype), new_id[d[eids]].to(g._dst.dtype), ids.numel())
+    sub.ndata = {k: v[ids] for k, v in g.ndata.items()}
+    sub.edata = {k: v[eids] for k, v in g.edata.items()}
+    if store_ids:
+        sub.ndata[NID], sub.edata[EID] = ids.to(g._src.dtype), eids.to(g._src.dtype)
+    return sub

@@ -3,6 +3,8 @@ OWN unmodified functions (``utils/data_utils.py:preprocess_graph``, ``train.py:g
 ``symmetry_loss``, ``get_bce_loss_full``, ``get_symmetry_loss_full``) over ``oracle/dgl_shim`` on CPU.
 
 TEST INFRASTRUCTURE.  Run in the build container only:  ``python -m oracle.make_golden_handoff``.
+Re-running reproduces every forward value bit for bit; the stored gradients move by ~1e-7 of their scale between runs
+(torch's threaded CPU backward of the index ops does not fix its summation order).
 Those modules cannot be imported whole here (Biopython, ``dgl.data``), so ``reference_runner.load_functions`` executes
 the functions' source with the module-level names supplied by hand.  ``add_positional_encoding`` needs scipy/``dgl.backend``
 only past its early return (``nb_pos_enc`` = 0, configs/hyperparameters.py:26); its two live lines
@@ -40,7 +42,8 @@ def main():
     ns = dict(torch=torch, F=F, dgl=dgl, get_hyperparameters=get_hyperparameters)
     rr.load_functions('utils/data_utils.py', {'preprocess_graph'}, ns)
     rr.load_functions('train.py', {'symmetry_loss', 'get_full_ne_features', 'get_bce_loss_full',
-                                   'get_symmetry_loss_full'}, ns)
+                                   'get_symmetry_loss_full', 'mask_graph_strandwise', 'get_partition_ne_features',
+                                   'get_bce_loss_partition', 'get_symmetry_loss_partition'}, ns)
     hp = get_hyperparameters()
     sd = torch.load(rr.weights_path(), weights_only=True)
 
@@ -88,6 +91,44 @@ def main():
                          buffers={k: b.clone() for k, b in mt.named_buffers()})
         print(name, 'loss', float(loss))
     torch.save(rec, os.path.join(OUT, 'handoff_losses.pt'))
+
+    # (c) strand-wise masking (train.py:91-100) and a mini-batch (train.py:125-135, 148-155, 173-185): induced
+    #     subgraphs with '_ID' maps, their features and losses.  dgl.node_subgraph is the shim's restatement of DGL's
+    #     documented behaviour; METIS is not involved -- the mini-batch is a contiguous block of nodes.
+    g, raw = build(1200, 7200, 29)
+    torch.manual_seed(5)
+    with rr.quiet():
+        masked = ns['mask_graph_strandwise'](g, 0.8, 'cpu')
+    keep = torch.zeros(g.num_nodes(), dtype=torch.bool)
+    keep[masked.ndata['_ID'].long()] = True
+    rec = dict(raw=raw, pos_weight=float(pos_weight), alpha=alpha, mask_keep=keep,
+               mask_node_id=masked.ndata['_ID'], mask_edge_id=masked.edata['_ID'],
+               mask_src=masked.edges()[0], mask_dst=masked.edges()[1],
+               mask_in_deg=masked.ndata['in_deg'], mask_e=masked.edata['e'], mask_y=masked.edata['y'])
+
+    def losses(fn, *args):
+        mt = models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch', dropout=None)
+        mt.load_state_dict(sd, strict=True)
+        mt.train()
+        seen = []
+        hook = mt.register_forward_hook(lambda mod, inp, out: seen.append(out.detach().squeeze(-1).clone()))
+        with rr.quiet():
+            loss, logits = ns[fn](*args[:-1], mt, *args[-1])
+        hook.remove()
+        return dict(loss=loss.detach(), logits=logits.detach(), forwards=seen)
+
+    rec['mask_sym'] = losses('get_symmetry_loss_full', masked, (pos_weight, alpha, 'cpu'))
+    batch_keep = torch.zeros(g.num_nodes(), dtype=torch.bool)
+    batch_keep[300:700] = True
+    sub = dgl.node_subgraph(g, batch_keep, store_ids=True)
+    x_b, e_b = ns['get_partition_ne_features'](sub, g, reverse=False)
+    rec.update(batch_keep=batch_keep, batch_node_id=sub.ndata['_ID'], batch_edge_id=sub.edata['_ID'],
+               batch_x=x_b, batch_e=e_b,
+               batch_bce=losses('get_bce_loss_partition', sub, g, (pos_weight, 'cpu')),
+               batch_sym=losses('get_symmetry_loss_partition', sub, g, (pos_weight, alpha, 'cpu')))
+    torch.save(rec, os.path.join(OUT, 'handoff_subgraphs.pt'))
+    print('masked', masked.num_nodes(), masked.num_edges(), 'loss', float(rec['mask_sym']['loss']),
+          '| batch', sub.num_nodes(), sub.num_edges(), float(rec['batch_bce']['loss']), float(rec['batch_sym']['loss']))
 
 
 if __name__ == '__main__':

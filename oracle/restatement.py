@@ -244,3 +244,21 @@ def symmetry_loss(org_scores, rev_scores, labels, pos_weight, alpha):
     """train.py:103-109."""
     bce = lambda s: F.binary_cross_entropy_with_logits(s, labels, pos_weight=pos_weight, reduction='none')  # noqa: E731
     return (bce(org_scores) + bce(rev_scores) + alpha * torch.abs(org_scores - rev_scores)).mean()
+
+
+def node_subgraph_ids(src, dst, n, keep):
+    """``dgl.node_subgraph(g, keep, store_ids=True)`` as train.py:95 uses it (DGL 0.8 documented behaviour): kept nodes
+    renumbered in increasing id order, induced edges in the order of their ids.
+    Returns (node_id, edge_id, sub_src, sub_dst) as int64 tensors."""
+    keep = keep.bool()
+    node_id = torch.nonzero(keep).flatten()
+    new_id = torch.cumsum(keep.long(), 0) - 1
+    s, d = src.long(), dst.long()
+    edge_id = torch.nonzero(keep[s] & keep[d]).flatten()
+    return node_id, edge_id, new_id[s[edge_id]], new_id[d[edge_id]]
+
+
+def partition_node_features(in_deg, out_deg, node_id, reverse=False):
+    """train.py:125-133: the parent's degrees at the batch's ``_ID``, z-scored within the batch."""
+    pe_in, pe_out = zscore(in_deg[node_id].unsqueeze(1)), zscore(out_deg[node_id].unsqueeze(1))
+    return torch.cat((pe_out, pe_in) if reverse else (pe_in, pe_out), dim=1)

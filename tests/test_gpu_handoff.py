@@ -183,3 +183,89 @@ def test_dataset_directory_like_graph_dataset(gnb, golden, tmp_path):
     idx, g = ds[1]
     assert g.num_edges() == gb.num_edges() and g.edata['e'].is_cuda and g.ndata['in_deg'].shape == (gb.num_nodes(),)
     torch.testing.assert_close(g.edata['e'].cpu(), golden('handoff_scores')['e'], rtol=5e-6, atol=5e-6)
+
+
+# ---- induced subgraphs: strand-wise masking and mini-batches -----------------------------
+
+def _check_losses(model_ctor, fn, ref, tol=1e-5):
+    """Run ``fn(model) -> (loss, logits)`` on a fresh train-mode model; compare loss / every forward with the fixture."""
+    model = model_ctor()
+    seen = []
+    hook = model.register_forward_hook(lambda mod, inp, out: seen.append(out.detach().squeeze(-1)))
+    loss, logits = fn(model)
+    hook.remove()
+    assert len(seen) == len(ref['forwards']) and logits.shape == ref['logits'].shape
+    for ours, theirs in zip(seen, ref['forwards']):
+        assert (torch.sigmoid(ours.cpu().double()) - torch.sigmoid(theirs.double())).abs().max().item() <= 1e-4
+    assert abs(loss.item() - ref['loss'].item()) <= tol * max(1.0, abs(ref['loss'].item()))
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_node_subgraph_bit_exact_vs_reference_masking(gnb, golden):
+    from gnnome_b200 import assembly as A
+    g = golden('handoff_subgraphs')
+    ag = _graph(g)
+    A.add_positional_encoding(A.preprocess_graph(ag))
+    sub = A.node_subgraph(ag, g['mask_keep'])
+    assert sub.num_nodes() == g['mask_node_id'].numel() and sub.num_edges() == g['mask_edge_id'].numel()
+    assert torch.equal(sub.ndata['_ID'].cpu(), g['mask_node_id']) and torch.equal(sub.edata['_ID'].cpu(), g['mask_edge_id'])
+    assert torch.equal(sub.edges()[0].cpu(), g['mask_src']) and torch.equal(sub.edges()[1].cpu(), g['mask_dst'])
+    assert torch.equal(sub.ndata['in_deg'].cpu(), g['mask_in_deg'])            # sliced from the parent, not recomputed
+    assert torch.equal(sub.edata['y'].cpu(), g['mask_y'])
+    torch.testing.assert_close(sub.edata['e'].cpu(), g['mask_e'], rtol=5e-6, atol=5e-6)
+    batch = A.node_subgraph(ag, g['batch_keep'])
+    assert torch.equal(batch.ndata['_ID'].cpu(), g['batch_node_id']) and torch.equal(batch.edata['_ID'].cpu(), g['batch_edge_id'])
+    x, e = A.get_partition_ne_features(batch, ag)
+    torch.testing.assert_close(x.cpu(), g['batch_x'], rtol=5e-6, atol=5e-6)
+    torch.testing.assert_close(e.cpu(), g['batch_e'], rtol=5e-6, atol=5e-6)
+
+
+@pytest.mark.parametrize('n,m,frac', [(1, 0, 1.0), (7, 30, 0.5), (1024, 4096, 0.0), (1024, 4096, 1.0),
+                                      (50_001, 300_007, 0.8), (2_000_000, 12_000_003, 0.85)])
+def test_node_subgraph_properties(gnb, n, m, frac):
+    """Sizes straddling the 1024-item blocks, empty and full masks, and a 12 M-edge graph: against torch on the device."""
+    from gnnome_b200 import ops
+    gen = torch.Generator(device='cuda').manual_seed(n + m)
+    src = torch.randint(0, n, (m,), device='cuda', generator=gen, dtype=torch.int32)
+    dst = torch.randint(0, n, (m,), device='cuda', generator=gen, dtype=torch.int32)
+    keep = torch.rand(n, device='cuda', generator=gen) < frac
+    node_id, edge_id, s, d = ops.node_subgraph(keep, src, dst, n)
+    want_nodes = torch.nonzero(keep).flatten()
+    ek = keep[src.long()] & keep[dst.long()]
+    want_edges = torch.nonzero(ek).flatten()
+    assert torch.equal(node_id.long(), want_nodes) and torch.equal(edge_id.long(), want_edges)
+    assert node_id.dtype == torch.int32 and s.dtype == torch.int32
+    if want_edges.numel():
+        assert torch.equal(node_id[s.long()], src[want_edges]) and torch.equal(node_id[d.long()], dst[want_edges])
+
+
+def test_mask_graph_strandwise_keeps_strand_pairs(gnb, golden):
+    from gnnome_b200 import assembly as A
+    ag = _graph(golden('handoff_subgraphs'))
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    sub = A.mask_graph_strandwise(ag, 0.8, generator=gen)
+    ids = sub.ndata['_ID'].cpu()
+    assert ids.numel() % 2 == 0 and torch.equal(ids[0::2] + 1, ids[1::2]) and bool((ids[0::2] % 2 == 0).all())
+    assert 0.7 < ids.numel() / ag.num_nodes() < 0.9
+    assert torch.equal(sub.edata['y'].cpu(), ag.edata['y'][sub.edata['_ID'].cpu().long()])
+    assert A.mask_graph_strandwise(ag, 1.0).num_edges() == ag.num_edges()
+
+
+def test_losses_on_masked_graph_and_mini_batch(gnb, golden, shipped_weights):
+    from gnnome_b200 import assembly as A
+    g = golden('handoff_subgraphs')
+    ag = _graph(g)
+    A.add_positional_encoding(A.preprocess_graph(ag))
+    pw = torch.tensor([g['pos_weight']], device='cuda')
+
+    def ctor():
+        m = gnb.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch', dropout=None)
+        m.load_state_dict(shipped_weights, strict=True)
+        return m.cuda().train()
+
+    masked = A.node_subgraph(ag, g['mask_keep'])
+    _check_losses(ctor, lambda m: A.get_symmetry_loss_full(masked, m, pw, g['alpha']), g['mask_sym'])
+    batch = A.node_subgraph(ag, g['batch_keep'])
+    _check_losses(ctor, lambda m: A.get_bce_loss_partition(batch, ag, m, pw), g['batch_bce'])
+    _check_losses(ctor, lambda m: A.get_symmetry_loss_partition(batch, ag, m, pw, g['alpha']), g['batch_sym'])

@@ -105,3 +105,21 @@ def test_feature_code_needs_the_gpu():
     ag = AssemblyGraph([0], [0], 1, dict(overlap_length=torch.tensor([5]), overlap_similarity=torch.tensor([1.0])))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         preprocess_graph(ag)
+
+
+def test_oracle_subgraphs_match_reference_masking(golden):
+    """Strand-wise masking (train.py:91-100) and a mini-batch (train.py:125-135) from the reference's own functions."""
+    g = golden('handoff_subgraphs')
+    src, dst, n, ol_len, ol_sim, y = _raw(g)
+    keep = g['mask_keep']
+    assert torch.equal(keep[0::2], keep[1::2])                     # both strands of a read go together
+    node_id, edge_id, s, d = R.node_subgraph_ids(src, dst, n, keep)
+    assert torch.equal(node_id, g['mask_node_id'].long()) and torch.equal(edge_id, g['mask_edge_id'].long())
+    assert torch.equal(s, g['mask_src'].long()) and torch.equal(d, g['mask_dst'].long())
+    assert torch.equal(R.edge_input_features(ol_len, ol_sim)[edge_id], g['mask_e'])      # features are sliced,
+    assert torch.equal(torch.bincount(dst.long(), minlength=n).float()[node_id], g['mask_in_deg'])  # not recomputed
+    node_id, edge_id, _, _ = R.node_subgraph_ids(src, dst, n, g['batch_keep'])
+    assert torch.equal(node_id, g['batch_node_id'].long()) and torch.equal(edge_id, g['batch_edge_id'].long())
+    ind, outd = torch.bincount(dst.long(), minlength=n).float(), torch.bincount(src.long(), minlength=n).float()
+    assert torch.equal(R.partition_node_features(ind, outd, node_id), g['batch_x'])
+    assert torch.equal(R.edge_input_features(ol_len, ol_sim)[edge_id], g['batch_e'])
