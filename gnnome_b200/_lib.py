@@ -65,7 +65,7 @@ SIGNATURES = {
     'gnb_t_agg_bwd_node': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _P, _P, _I, _P, _L, _P]),
     'gnb_t_gate_fwd': (_I, [_P, _P, _L, _I, _P, _P, _P]),
     'gnb_t_gate_bwd': (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P]),
-    'gnb_t_affine2': (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    'gnb_t_affine2': (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P]),
     'gnb_t_layer_norm_fwd': (_I, [_P, _P, _P, _L, _I, ctypes.c_float, _P, _P, _P, _P]),
     'gnb_t_layer_norm_bwd': (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
     'gnb_t_col_stats_workspace': (_S, [_L, _I]),

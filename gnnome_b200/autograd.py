@@ -129,11 +129,15 @@ def _col_stats(a, b=None, shift_a=None, shift_b=None):
     return out
 
 
-def _affine2(x, y, a, b, c):
+def _affine2(x, y, a, b, c, shift_x=None, shift_y=None):
+    """a * (x - shift_x) (+ b * (y - shift_y)) + c per channel; the fp64 coefficient vectors are rounded to fp32 here."""
     rows, W = x.shape
     out = torch.empty_like(x)
-    _call('gnb_t_affine2', x.device, x.data_ptr(), None if y is None else y.data_ptr(), a.data_ptr(),
-          None if b is None else b.data_ptr(), c.data_ptr(), rows, W, out.data_ptr())
+    f32 = lambda t: None if t is None else t.float().contiguous()  # noqa: E731
+    a, b, c, shift_x, shift_y = (f32(t) for t in (a, b, c, shift_x, shift_y))
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    _call('gnb_t_affine2', x.device, x.data_ptr(), ptr(y), a.data_ptr(), ptr(b), c.data_ptr(), ptr(shift_x), ptr(shift_y),
+          rows, W, out.data_ptr())
     return out
 
 
@@ -151,10 +155,12 @@ class BatchNormTrain(torch.autograd.Function):
         mean = mean32.double() + st[0] / n
         var = (st[1] / n - (st[0] / n) ** 2).clamp_min_(0.0)
         rstd = torch.rsqrt(var + eps)
+        # y = a * (x - mean) + bias, centred on the fp32 first-pass mean (its fp64 correction goes into the constant):
+        # a * x + (bias - a * mean) loses the digits of a channel whose mean is large against its spread
         a = weight.detach().double() * rstd
-        c = bias.detach().double() - mean * a
-        y = _affine2(x, None, a.float().contiguous(), None, c.float().contiguous())
-        ctx.save_for_backward(x, weight, mean, rstd)
+        c = bias.detach().double() - (mean - mean32.double()) * a
+        y = _affine2(x, None, a, None, c, shift_x=mean32)
+        ctx.save_for_backward(x, weight, mean, rstd, mean32)
         ctx.n = n
         mean_f, var_f = mean.float(), var.float()
         ctx.mark_non_differentiable(mean_f, var_f)
@@ -162,17 +168,18 @@ class BatchNormTrain(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gm, _gv):
-        x, weight, mean, rstd = ctx.saved_tensors
+        x, weight, mean, rstd, mean32 = ctx.saved_tensors
         n = ctx.n
         g = _c(g)
-        st = _col_stats(g, x, shift_b=mean.float().contiguous())       # sum g, sum g * (x - mean)
+        st = _col_stats(g, x, shift_b=mean32)                           # sum g, sum g * (x - mean32)
         c1 = st[0]
-        c2 = rstd * st[1]                                               # sum g * xhat
+        c2 = rstd * (st[1] - (mean - mean32.double()) * c1)             # sum g * xhat
         w = weight.detach().double()
         a = w * rstd
         b = -w * rstd * rstd * c2 / n
-        c = -a * c1 / n - b * mean
-        gx = _affine2(g, x, a.float().contiguous(), b.float().contiguous(), c.float().contiguous())
+        # gx = a * (g - mean(g)) + b * (x - mean): centred like the forward (torch's backward centres x too)
+        c = -a * c1 / n + b * (mean32.double() - mean)
+        gx = _affine2(g, x, a, b, c, shift_y=mean32)
         return gx, c2.to(weight.dtype), c1.to(weight.dtype), None
 
 

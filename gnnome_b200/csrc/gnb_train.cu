@@ -180,16 +180,26 @@ __global__ void gate_bwd_kernel(const float* __restrict__ g_e, const float* __re
   }
 }
 
-// out = a * x (+ b * y) + c with per-channel a, b, c: BatchNorm normalise (y = null) and its input gradient
+// out = a * (x - sx) (+ b * (y - sy)) + c with per-channel a, b, c, sx, sy: BatchNorm normalise (y = null) and its input
+// gradient.  The shifts (null = 0) are the column means: a channel whose mean is large against its spread would lose
+// its digits in a * x + (c - a * mean).
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
 __global__ void affine2_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ a,
-                               const float* __restrict__ b, const float* __restrict__ cc, int64_t rows, int H,
-                               float* __restrict__ out) {
+                               const float* __restrict__ b, const float* __restrict__ cc, const float* __restrict__ sx,
+                               const float* __restrict__ sy, int64_t rows, int H, float* __restrict__ out) {
   const int h4 = H / 4;
   const int64_t total = rows * h4;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % h4) * 4;
-    float4 v = fma4(ld4(a + c), ld4(x + 4 * i), ld4(cc + c));
-    if (y) v = fma4(ld4(b + c), ld4(y + 4 * i), v);
+    float4 xv = ld4(x + 4 * i);
+    if (sx) xv = sub4(xv, ld4(sx + c));
+    float4 v = fma4(ld4(a + c), xv, ld4(cc + c));
+    if (y) {
+      float4 yv = ld4(y + 4 * i);
+      if (sy) yv = sub4(yv, ld4(sy + c));
+      v = fma4(ld4(b + c), yv, v);
+    }
     st4(out + 4 * i, v);
   }
 }
@@ -386,12 +396,12 @@ extern "C" int gnb_t_gate_bwd(const float* g_e, const float* g_sigma, const floa
   return check_launch("gnb_t_gate_bwd");
 }
 
-extern "C" int gnb_t_affine2(const float* x, const float* y, const float* a, const float* b, const float* c, int64_t rows,
-                             int H, float* out, void* stream) {
+extern "C" int gnb_t_affine2(const float* x, const float* y, const float* a, const float* b, const float* c,
+                             const float* shift_x, const float* shift_y, int64_t rows, int H, float* out, void* stream) {
   GNB_REQUIRE(H > 0 && H % 4 == 0, "hidden_features=%d must be a positive multiple of 4", H);
   if (rows == 0) return 0;
   GNB_REQUIRE(x && a && c && out && (y == nullptr || b != nullptr), "null pointer");
-  affine2_kernel<<<blocks_for(rows * (H / 4)), kT, 0, (cudaStream_t)stream>>>(x, y, a, b, c, rows, H, out);
+  affine2_kernel<<<blocks_for(rows * (H / 4)), kT, 0, (cudaStream_t)stream>>>(x, y, a, b, c, shift_x, shift_y, rows, H, out);
   return check_launch("gnb_t_affine2");
 }
 

@@ -259,9 +259,11 @@ int gnb_t_gate_fwd(const float* ehat, const float* e_in, int64_t rows, int H, fl
 /* t = g_e + g_sigma * sigma * (1 - sigma); g_ehat = t * [ehat > 0]; g_ein = t (if not NULL) */
 int gnb_t_gate_bwd(const float* g_e, const float* g_sigma, const float* ehat, const float* sigma, int64_t rows,
                    int H, float* g_ehat, float* g_ein, void* stream);
-/* out = a * x (+ b * y) + c with per-channel a, b, c: BatchNorm normalise (y NULL) and its input gradient */
-int gnb_t_affine2(const float* x, const float* y, const float* a, const float* b, const float* c, int64_t rows,
-                  int H, float* out, void* stream);
+/* out = a * (x - shift_x) (+ b * (y - shift_y)) + c with per-channel a, b, c and shifts (NULL = 0): BatchNorm normalise
+ * (y NULL) and its input gradient.  The shifts carry the column means, so that a channel whose mean is large against its
+ * spread keeps its digits (torch centres before scaling in the backward too). */
+int gnb_t_affine2(const float* x, const float* y, const float* a, const float* b, const float* c, const float* shift_x,
+                  const float* shift_y, int64_t rows, int H, float* out, void* stream);
 /* nn.LayerNorm over the W channels of each row (gated_gcn_full.py:39-42): y = gamma * xhat + beta with
  * xhat = (x - mean_row) / sqrt(var_row + eps) (biased variance); xhat [rows][W] and rstd [rows] are kept for the backward */
 int gnb_t_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int W, float eps,

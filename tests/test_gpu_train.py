@@ -92,6 +92,37 @@ def test_batchnorm_train_matches_torch(gnb):
     assert int(bn1.num_batches_tracked) == 2
 
 
+def test_batchnorm_train_offset_channels_vs_fp64(gnb):
+    """Channels whose mean is large against their spread (|mean| / std up to 1e4, as trained GNNome layers produce on
+    some inputs): forward and input gradient must keep fp32 accuracy relative to an fp64 BatchNorm -- the affine passes
+    are centred on the column mean (a * x + (c - a * mean) lost 2-3 digits here)."""
+    from gnnome_b200 import autograd as ag
+    torch.manual_seed(1)
+    rows, W = 4000, 64
+    spread = torch.logspace(-3, 0.5, W, device='cuda')
+    offset = torch.linspace(-30, 30, W, device='cuda')
+    x = (torch.randn(rows, W, device='cuda') * spread + offset).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(W).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+    w = torch.randn(rows, W, device='cuda')
+    y = ag.batch_norm(bn, x, True)
+    (y * w).sum().backward()
+    x64 = x.detach().double().requires_grad_(True)
+    bn64 = torch.nn.BatchNorm1d(W).cuda().double()
+    with torch.no_grad():
+        bn64.weight.copy_(bn.weight); bn64.bias.copy_(bn.bias)
+    y64 = bn64(x64)
+    (y64 * w.double()).sum().backward()
+    # both sides see the same fp32 x and x - mean is exact in fp32 (Sterbenz), so no channel may be worse than ~1e-6;
+    # the uncentred form was off by 2e-3 in the channels with |mean| / std ~ 1e4
+    assert (y.double() - y64).abs().max().item() <= 2e-5
+    gscale = x64.grad.abs().max(0).values
+    assert ((x.grad.double() - x64.grad).abs().max(0).values <= 5e-5 * gscale).all()
+    torch.testing.assert_close(bn.weight.grad.double(), bn64.weight.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(bn.bias.grad.double(), bn64.bias.grad, rtol=1e-4, atol=1e-3)
+
+
 def test_training_step_vs_reference_golden(gnb, golden, shipped_weights):
     g = golden('sym_shipped_trainstep')
     model = gnb.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch', dropout=None)
