@@ -26,6 +26,12 @@ class GnbGraph(ctypes.Structure):
     ]
 
 
+class GnbWalkGraph(ctypes.Structure):
+    """Mirror of ``gnb_walk_graph_t`` (host pointers)."""
+    _fields_ = [('num_nodes', ctypes.c_int64), ('succ_ptr', ctypes.c_void_p), ('succ_node', ctypes.c_void_p),
+                ('succ_edge', ctypes.c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/gnnome_b200.h
 _P, _I, _L, _S = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
 SIGNATURES = {
@@ -79,9 +85,12 @@ SIGNATURES = {
     'gnb_subgraph_workspace': (_I, [_L, _L, ctypes.POINTER(_S)]),
     'gnb_subgraph_count': (_I, [_P, _P, _P, _L, _L, _P, _S, _P, _P]),
     'gnb_subgraph_fill': (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P]),
+    'gnb_greedy_walks': (_I, [ctypes.POINTER(GnbWalkGraph), _P, _P, _L, _P, _P, _I, _P, _L, _P, _P, _P]),
+    'gnb_walk_contig_length': (_I, [ctypes.POINTER(GnbWalkGraph), _P, _P, _P, _L, _P]),
+    'gnb_walk_jumped_nodes': (_I, [ctypes.POINTER(GnbWalkGraph), ctypes.POINTER(GnbWalkGraph), _P, _L, _P]),
 }
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 

@@ -1,0 +1,143 @@
+"""Greedy decoder walks -- the step after the scoring pass (reference inference.py:70-164,
+231-322).  Host-side: the walks are sequential pointer chasing over a few successors per node, so they run in C++ on the
+CPU (``csrc/gnb_walks.cu``), the ``nb_paths`` candidates of one iteration on a pool of threads.
+
+``WalkGraph`` holds the reference's ``succs`` / ``preds`` / ``edges`` structures ({idx}_succ.pkl, {idx}_pred.pkl,
+{idx}_edges.pkl, inference.py:445-455) as CSR arrays and offers the reference's functions on them:
+
+* ``run_greedy_both_ways`` for a whole batch of start edges (inference.py:164-168 inside the loop of :231-247),
+* ``get_contig_length`` (:30-37), and the jumped-over nodes of an accepted walk (:316-322).
+
+Results are identical to the reference's: the same walks node for node, and the same float32 ``sumLogProb`` bit for bit
+(``RANDOM`` and ``early_stopping`` are off, as shipped).  Exact ties between successors go to the first in list order,
+which is torch's choice for up to 16 candidates."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _np(t, dtype):
+    if torch.is_tensor(t):
+        t = t.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(t), dtype=dtype)
+
+
+def _csr_from_dicts(num_nodes, lists, edge_of=None):
+    counts = np.zeros(num_nodes, dtype=np.int64)
+    for i, nbrs in lists.items():
+        counts[i] = len(nbrs)
+    ptr = np.zeros(num_nodes + 1, dtype=np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    node = np.empty(int(ptr[-1]), dtype=np.int32)
+    edge = np.zeros(int(ptr[-1]), dtype=np.int32)
+    for i, nbrs in lists.items():
+        if len(nbrs):
+            node[ptr[i]:ptr[i + 1]] = nbrs
+            if edge_of is not None:
+                edge[ptr[i]:ptr[i + 1]] = [edge_of[(i, int(v))] for v in nbrs]
+    return ptr, node, edge
+
+
+def _csr_from_edges(key_nodes, other_nodes, eids, num_nodes):
+    order = np.argsort(key_nodes, kind='stable')               # lists in edge-id order
+    ptr = np.zeros(num_nodes + 1, dtype=np.int64)
+    np.cumsum(np.bincount(key_nodes, minlength=num_nodes), out=ptr[1:])
+    return ptr, other_nodes[order].astype(np.int32), eids[order].astype(np.int32)
+
+
+class WalkGraph:
+    """CSR view of ``succs`` (node -> list of successors), ``preds`` and ``edges`` ((u, v) -> edge id)."""
+
+    def __init__(self, num_nodes, succ_csr, pred_csr=None):
+        self.N = int(num_nodes)
+        if self.N % 2:
+            raise ValueError('nodes come in strand pairs (2k, 2k + 1): num_nodes must be even')
+        self._succ, self._pred = succ_csr, pred_csr
+        self._lib = _lib.load()
+
+    @classmethod
+    def from_dicts(cls, num_nodes, succs, edges, preds=None):
+        """From the reference's pickled dicts ({idx}_succ.pkl, {idx}_edges.pkl, {idx}_pred.pkl)."""
+        return cls(num_nodes, _csr_from_dicts(num_nodes, succs, edges),
+                   None if preds is None else _csr_from_dicts(num_nodes, preds))
+
+    @classmethod
+    def from_edge_list(cls, src, dst, num_nodes):
+        """succs / preds in edge-id order and ``edges[(u, v)]`` = the LAST edge id of that pair (a dict filled in edge
+        order keeps the last write), without Python loops."""
+        src, dst = _np(src, np.int64), _np(dst, np.int64)
+        eid = np.arange(src.size, dtype=np.int64)
+        _, inverse = np.unique(src * int(num_nodes) + dst, return_inverse=True)
+        last = np.zeros(int(inverse.max()) + 1 if src.size else 0, dtype=np.int64)
+        np.maximum.at(last, inverse, eid)
+        pair_eid = last[inverse] if src.size else eid
+        return cls(num_nodes, _csr_from_edges(src, dst, pair_eid, num_nodes), _csr_from_edges(dst, src, pair_eid, num_nodes))
+
+    def _struct(self, csr):
+        ptr, node, edge = csr
+        return _lib.GnbWalkGraph(self.N, ptr.ctypes.data, node.ctypes.data, edge.ctypes.data)
+
+    def _visited_bytes(self, visited):
+        if visited is None:
+            return None
+        if isinstance(visited, (set, frozenset, list, tuple)):
+            v = np.zeros(self.N, dtype=np.uint8)
+            if len(visited):
+                v[np.fromiter(visited, dtype=np.int64, count=len(visited))] = 1
+            return v
+        v = _np(visited, np.uint8)
+        if v.shape != (self.N,):
+            raise ValueError('visited must be a set of nodes or an (N,) mask')
+        return v
+
+    def run_greedy_both_ways(self, candidates, log_probs, visited=None, threads=0):
+        """For every start edge ``(src, dst)`` in ``candidates``: ``(walk_f, walk_b, sumLogProb_f, sumLogProb_b)`` of
+        ``run_greedy_both_ways(src, dst, logProbs, succs, preds, edges, visited)`` (inference.py:164-168); the sums are
+        float32 scalars (numpy).  ``visited``: a set of nodes or an (N,) mask."""
+        cand = _np(candidates, np.int32).reshape(-1, 2)
+        n = cand.shape[0]
+        src, dst = np.ascontiguousarray(cand[:, 0]), np.ascontiguousarray(cand[:, 1])
+        logp = _np(log_probs, np.float32).reshape(-1)
+        vis = self._visited_bytes(visited)
+        off = np.zeros(n + 1, dtype=np.int64)
+        back = np.zeros(max(n, 1), dtype=np.int64)
+        sums = np.zeros((max(n, 1), 2), dtype=np.float32)
+        g = self._struct(self._succ)
+        args = lambda buf: (ctypes.byref(g), logp.ctypes.data, None if vis is None else vis.ctypes.data, n,  # noqa: E731
+                            src.ctypes.data, dst.ctypes.data, int(threads), buf.ctypes.data, buf.size, off.ctypes.data,
+                            back.ctypes.data, sums.ctypes.data)
+        buf = np.empty(max(4096, 64 * n), dtype=np.int32)
+        rc = self._lib.gnb_greedy_walks(*args(buf))
+        if rc == -2:                                    # GNB_E_WORKSPACE: off[n] holds the size needed
+            buf = np.empty(int(off[n]), dtype=np.int32)
+            rc = self._lib.gnb_greedy_walks(*args(buf))
+        _lib.check(rc, 'gnb_greedy_walks')
+        out = []
+        for k in range(n):
+            w = buf[off[k]:off[k + 1]]
+            out.append((w[back[k]:].tolist(), w[:back[k]].tolist(), sums[k, 0], sums[k, 1]))
+        return out
+
+    def get_contig_length(self, walk, prefix_length, read_length):
+        """inference.py:30-37: sum of ``prefix_length`` over the walk's edges + ``read_length`` of its last node."""
+        w = _np(walk, np.int32)
+        pl, rl = _np(prefix_length, np.int64), _np(read_length, np.int64)
+        out = ctypes.c_int64(0)
+        g = self._struct(self._succ)
+        _lib.check(self._lib.gnb_walk_contig_length(ctypes.byref(g), pl.ctypes.data, rl.ctypes.data, w.ctypes.data, w.size,
+                                                    ctypes.byref(out)), 'gnb_walk_contig_length')
+        return out.value
+
+    def jumped_nodes(self, walk):
+        """inference.py:316-322: the set ``trans`` of nodes an accepted walk jumps over (and their complements)."""
+        if self._pred is None:
+            raise ValueError('jumped_nodes needs the predecessor lists')
+        w = _np(walk, np.int32)
+        mark = np.zeros(self.N, dtype=np.uint8)
+        gs, gp = self._struct(self._succ), self._struct(self._pred)
+        _lib.check(self._lib.gnb_walk_jumped_nodes(ctypes.byref(gs), ctypes.byref(gp), w.ctypes.data, w.size,
+                                                   mark.ctypes.data), 'gnb_walk_jumped_nodes')
+        return set(np.nonzero(mark)[0].tolist())

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 7
+#define GNB_ABI_VERSION 8
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -310,6 +310,32 @@ int gnb_subgraph_count(const uint8_t* keep, const int32_t* src, const int32_t* d
 int gnb_subgraph_fill(const uint8_t* keep, const int32_t* src, const int32_t* dst, int64_t num_nodes, int64_t num_edges,
                       void* workspace, int32_t* node_id, int32_t* edge_id, int32_t* sub_src, int32_t* sub_dst,
                       void* stream);
+
+/* ---- greedy decoder walks: HOST functions, host pointers (inference.py:70-164, 231-305) ---------------------------------
+ * The step after the scoring pass.  Successor lists as a CSR in the order of the reference's succs[i] lists (the order
+ * decides exact ties), succ_edge[q] = edges[(i, succ_node[q])]; nodes come in strand pairs (2k, 2k + 1). */
+typedef struct gnb_walk_graph {
+  int64_t num_nodes;
+  const int64_t* succ_ptr;   /* [N+1] */
+  const int32_t* succ_node;  /* [sum of list lengths] */
+  const int32_t* succ_edge;  /* [same] edge id of (i, succ_node[q]) */
+} gnb_walk_graph_t;
+/* run_greedy_both_ways (inference.py:164-168) for n_cand start edges against one shared visited map (bytes, NULL =
+ * nothing visited), RANDOM / early_stopping off as shipped (:25-28): walk k = walk_buf[walk_off[k] .. walk_off[k+1]) =
+ * walk_b + walk_f, back_len[k] = len(walk_b), sum_logp[2k], [2k+1] = sumLogProb_f, sumLogProb_b accumulated in fp32 in
+ * the reference's order (bit-equal).  log_probs[eid] = log(sigmoid(score)) (:184).  threads <= 0: all hardware threads.
+ * Returns GNB_E_WORKSPACE with walk_off filled when walk_cap < walk_off[n_cand]: size the buffer and call again. */
+int gnb_greedy_walks(const gnb_walk_graph_t* g, const float* log_probs, const uint8_t* visited, int64_t n_cand,
+                     const int32_t* cand_src, const int32_t* cand_dst, int threads, int32_t* walk_buf, int64_t walk_cap,
+                     int64_t* walk_off, int64_t* back_len, float* sum_logp);
+/* get_contig_length (inference.py:30-37): sum of prefix_length over the walk's edges + read_length of its last node */
+int gnb_walk_contig_length(const gnb_walk_graph_t* g, const int64_t* prefix_length, const int64_t* read_length,
+                           const int32_t* walk, int64_t len, int64_t* out);
+/* The "jumped-over" nodes of an accepted walk (inference.py:316-322): for consecutive (ss, dd), every t in
+ * succs[ss] & preds[dd] and its complement t ^ 1 get mark[t] = 1 (mark [N] bytes, not cleared).  pred: the CSR of the
+ * predecessor lists (succ_edge unused). */
+int gnb_walk_jumped_nodes(const gnb_walk_graph_t* succ, const gnb_walk_graph_t* pred, const int32_t* walk, int64_t len,
+                          uint8_t* mark);
 
 #ifdef __cplusplus
 }

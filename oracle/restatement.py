@@ -262,3 +262,52 @@ def partition_node_features(in_deg, out_deg, node_id, reverse=False):
     """train.py:125-133: the parent's degrees at the batch's ``_ID``, z-scored within the batch."""
     pe_in, pe_out = zscore(in_deg[node_id].unsqueeze(1)), zscore(out_deg[node_id].unsqueeze(1))
     return torch.cat((pe_out, pe_in) if reverse else (pe_in, pe_out), dim=1)
+
+
+# ---- greedy decoder walks (SURVEY.md section 8(f) row 4) -- pure-Python loops, small cases only ---------------------------
+
+def greedy_walk(start, log_probs, succs, edges, visited_old):
+    """inference.py:70-114 (``greedy_forwards``; ``greedy_backwards_rc`` :117-161 is the same loop from ``start ^ 1``)
+    with ``RANDOM`` and ``early_stopping`` off (:25-28).  Returns (walk, visited, float32 sum of log-probabilities)."""
+    current, walk, visited = start, [], set()
+    total = torch.zeros(1, dtype=torch.float32)
+    while True:
+        walk.append(current)
+        visited.update((current, current ^ 1))
+        nbrs = succs.get(current, [])
+        if len(nbrs) == 1:
+            if nbrs[0] in visited_old or nbrs[0] in visited:
+                break
+            total += log_probs[edges[current, nbrs[0]]]
+            current = nbrs[0]
+            continue
+        free = [v for v in nbrs if not (v in visited_old or v in visited)]
+        if not free:
+            break
+        p = log_probs[[edges[current, v] for v in free]]
+        best = int(torch.argmax(p))            # torch.topk(k=1): first of equal maxima for short lists
+        total += p[best]
+        current = free[best]
+    return walk, visited, total
+
+
+def run_greedy_both_ways(src, dst, log_probs, succs, edges, visited):
+    """inference.py:164-168 -> (walk_f, walk_b, sumLogProb_f, sumLogProb_b)."""
+    tmp = set(visited) | {src, src ^ 1, dst, dst ^ 1}
+    walk_f, vis_f, sum_f = greedy_walk(dst, log_probs, succs, edges, tmp)
+    walk_b, _, sum_b = greedy_walk(src ^ 1, log_probs, succs, edges, tmp | vis_f)
+    return walk_f, [w ^ 1 for w in reversed(walk_b)], sum_f, sum_b
+
+
+def contig_length(walk, edges, prefix_length, read_length):
+    """inference.py:30-37 (``graph.edges[u, v].data['prefix_length']`` looked up through the ``edges`` dict)."""
+    return int(sum(int(prefix_length[edges[u, v]]) for u, v in zip(walk[:-1], walk[1:])) + int(read_length[walk[-1]]))
+
+
+def jumped_nodes(walk, succs, preds):
+    """inference.py:316-322: nodes between consecutive walk nodes (successor of one, predecessor of the next), both strands."""
+    trans = set()
+    for ss, dd in zip(walk[:-1], walk[1:]):
+        t1 = set(succs.get(ss, [])) & set(preds.get(dd, []))
+        trans |= t1 | {t ^ 1 for t in t1}
+    return trans

@@ -1,0 +1,91 @@
+"""Greedy decoder walks: the C++ walker and the oracle's restatement against walks produced
+by the reference's OWN ``greedy_forwards`` / ``greedy_backwards_rc`` / ``run_greedy_both_ways`` (oracle/make_golden_walks.py).
+Host code: runs without a GPU.  Bit-exact: the same nodes in the same order, the same float32 sums."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+
+
+@pytest.fixture(scope='module')
+def fx(golden):
+    g = golden('walks')
+    src, dst, n = g['src'], g['dst'], g['num_nodes']
+    succs, preds, edges = {}, {}, {}
+    for k, (u, v) in enumerate(zip(src.tolist(), dst.tolist())):
+        succs.setdefault(u, []).append(v)
+        preds.setdefault(v, []).append(u)
+        edges[(u, v)] = k
+    g.update(succs=succs, preds=preds, edges=edges, log_probs=torch.log(torch.sigmoid(g['scores'])))
+    return g
+
+
+@pytest.mark.parametrize('key,use_visited', [('results', True), ('results_nothing_visited', False)])
+def test_oracle_walks_match_reference_functions(fx, key, use_visited):
+    visited = set(fx['visited']) if use_visited else set()
+    for (s, d), ref in zip(fx['candidates'], fx[key]):
+        walk_f, walk_b, sum_f, sum_b = R.run_greedy_both_ways(s, d, fx['log_probs'], fx['succs'], fx['edges'], visited)
+        assert walk_f == ref['walk_f'] and walk_b == ref['walk_b']
+        assert torch.equal(sum_f, ref['sum_f']) and torch.equal(sum_b, ref['sum_b'])
+
+
+@pytest.mark.parametrize('build', ['edge_list', 'dicts'])
+@pytest.mark.parametrize('key,use_visited', [('results', True), ('results_nothing_visited', False)])
+@pytest.mark.parametrize('threads', [1, 4])
+def test_walker_bit_exact_vs_reference_functions(fx, build, key, use_visited, threads):
+    from gnnome_b200.decode import WalkGraph
+    n = fx['num_nodes']
+    wg = (WalkGraph.from_edge_list(fx['src'], fx['dst'], n) if build == 'edge_list'
+          else WalkGraph.from_dicts(n, fx['succs'], fx['edges'], fx['preds']))
+    visited = set(fx['visited']) if use_visited else None
+    res = wg.run_greedy_both_ways(fx['candidates'], fx['log_probs'], visited, threads=threads)
+    assert len(res) == len(fx[key])
+    for (walk_f, walk_b, sum_f, sum_b), ref in zip(res, fx[key]):
+        assert walk_f == ref['walk_f'] and walk_b == ref['walk_b']
+        assert np.float32(sum_f) == ref['sum_f'].numpy()[0] and np.float32(sum_b) == ref['sum_b'].numpy()[0]   # bit-equal
+        walk = walk_b + walk_f
+        assert len(set(walk) | {w ^ 1 for w in walk}) == ref['n_visited']
+        assert wg.get_contig_length(walk, fx['prefix_length'], fx['read_length']) == ref['contig_length']
+        assert sorted(wg.jumped_nodes(walk)) == ref['jumped']
+
+
+def test_walker_edge_cases(fx):
+    from gnnome_b200.decode import WalkGraph
+    # 0 -> 2 -> 4, 0 -> 6 (dead end), 4 has no successor; strand twins 1, 3, 5, 7 isolated
+    wg = WalkGraph.from_edge_list([0, 2, 0], [2, 4, 6], 8)
+    logp = torch.log(torch.tensor([0.9, 0.8, 0.1]))
+    (walk_f, walk_b, sum_f, sum_b), = wg.run_greedy_both_ways([(0, 2)], logp)
+    assert walk_f == [2, 4] and walk_b == [0] and sum_b == 0.0          # backward: start 0 ^ 1 = 1 has no successors
+    assert np.float32(sum_f) == np.float32(np.log(np.float32(0.8)))
+    assert wg.run_greedy_both_ways([], logp) == []
+    # visited as a mask; a visited successor stops the walk
+    mask = torch.zeros(8, dtype=torch.bool)
+    mask[4] = True
+    (walk_f, _, sum_f, _), = wg.run_greedy_both_ways([(0, 2)], logp, mask)
+    assert walk_f == [2] and sum_f == 0.0
+    # exact tie: the first successor in list order wins, as torch.topk does
+    wt = WalkGraph.from_edge_list([0, 0, 0], [2, 4, 6], 8)
+    (walk_f, _, _, _), = wt.run_greedy_both_ways([(1, 0)], torch.log(torch.tensor([0.5, 0.5, 0.5])))
+    assert walk_f == [0, 2]
+    with pytest.raises(ValueError, match='strand pairs'):
+        WalkGraph.from_edge_list([0], [1], 3)
+    with pytest.raises(RuntimeError, match='out of range'):
+        wg.run_greedy_both_ways([(0, 9)], logp)
+    with pytest.raises(RuntimeError, match='no edge'):
+        wg.get_contig_length([0, 4], torch.ones(3, dtype=torch.int64), torch.ones(8, dtype=torch.int64))
+    assert wg.get_contig_length([0, 2, 4], torch.tensor([5, 7, 11]), torch.arange(8) * 100) == 5 + 7 + 400
+
+
+def test_walker_long_walks_grow_the_buffer():
+    """A 20 000-node chain per strand: one candidate walks all of it (longer than the first buffer guess)."""
+    from gnnome_b200.decode import WalkGraph
+    n = 40_000
+    fwd = np.arange(0, n - 2, 2)                       # 0 -> 2 -> 4 ... on the even strand
+    rev = np.arange(n - 1, 1, -2)                      # n-1 -> n-3 -> ... on the odd strand (reverse complements)
+    src, dst = np.concatenate((fwd, rev)), np.concatenate((fwd + 2, rev - 2))
+    wg = WalkGraph.from_edge_list(src, dst, n)
+    logp = torch.zeros(src.size)
+    mid = n // 2
+    (walk_f, walk_b, _, _), = wg.run_greedy_both_ways([(mid, mid + 2)], logp)
+    assert walk_b + walk_f == list(range(0, n, 2))
