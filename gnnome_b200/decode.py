@@ -141,3 +141,88 @@ class WalkGraph:
         _lib.check(self._lib.gnb_walk_jumped_nodes(ctypes.byref(gs), ctypes.byref(gp), w.ctypes.data, w.size,
                                                    mark.ctypes.data), 'gnb_walk_jumped_nodes')
         return set(np.nonzero(mark)[0].tolist())
+
+
+def sample_edges(prob_edges, nb_paths, fast=False):
+    """inference.py:54-67: ``nb_paths`` start edges drawn from the categorical distribution over the remaining edges'
+    probabilities.  By default the same torch calls on the same tensors as the reference, so that a seeded run draws the
+    same edges -- at the reference's cost: ``Categorical(probs.repeat(nb_paths, 1)).sample()`` takes one sample per row
+    through torch's exponential-race path, i.e. nb_paths x E exponential variates per decoder iteration (5.5 s at 3 M
+    edges and 50 paths).  ``fast=True`` draws the nb_paths samples from the one distribution (inverse-CDF, 25 ms there):
+    the same distribution, different random numbers."""
+    if prob_edges.shape[0] > 2 ** 24:           # torch.distributions.Categorical stops at 2**24 categories (:56-57)
+        prob_edges = prob_edges[:2 ** 24]
+    prob_edges = prob_edges.masked_fill(prob_edges < 1e-9, 1e-9)
+    prob_edges = prob_edges / prob_edges.sum()
+    if fast:
+        return torch.multinomial(prob_edges, nb_paths, replacement=True)
+    return torch.distributions.categorical.Categorical(prob_edges.repeat(nb_paths, 1)).sample()
+
+
+def get_contigs_greedy(g, succs, preds, edges, len_threshold, nb_paths=50, use_labels=False, checkpoint_dir=None,
+                       load_checkpoint=False, threads=0, fast_sampling=False):
+    """``get_contigs_greedy`` (inference.py:167-361): repeat { drop the visited nodes, sample ``nb_paths`` start edges from
+    what is left, walk greedily both ways from each, keep the candidate with the longest contig, mark it (and the nodes
+    it jumps over) visited } until no edge is left or the best contig is shorter than ``len_threshold``.  Returns the
+    list of walks.  ``g``: anything with ``edges()``, ``num_nodes()``, ``edata['score' | 'y', 'prefix_length']`` and
+    ``ndata['read_length']`` (a DGLGraph, an ``AssemblyGraph``).  With the same torch seed the result is the reference's,
+    walk for walk; its progress prints are not reproduced.  Checkpoints (every 10 contigs) use the reference's pickle.
+    ``fast_sampling``: see ``sample_edges`` (gives up the identical random draws for a much cheaper iteration)."""
+    import os
+    import pickle
+    n = g.num_nodes()
+    src, dst = (_np(t, np.int64) for t in g.edges())
+    wg = WalkGraph.from_dicts(n, succs, edges, preds)
+    if use_labels:                                                      # :179-182
+        prob_all = g.edata['y'].detach().cpu().float()
+        log_probs = torch.log(prob_all.masked_fill(prob_all < 1e-9, 1e-9))
+    else:                                                               # :183-184
+        score = g.edata['score'].detach().cpu()
+        prob_all = torch.sigmoid(score)
+        log_probs = torch.log(torch.sigmoid(score))
+    prob_all = prob_all.reshape(-1)
+    prefix_length, read_length = g.edata['prefix_length'], g.ndata['read_length']
+    all_contigs, all_walks_len, all_contigs_len = [], [], []
+    visited = np.zeros(n, dtype=bool)
+    ckpt_file = None if checkpoint_dir is None else os.path.join(checkpoint_dir, 'checkpoint.pkl')
+    if load_checkpoint and ckpt_file is not None and os.path.isfile(ckpt_file):        # :189-196
+        with open(ckpt_file, 'rb') as f:
+            ck = pickle.load(f)
+        all_contigs, all_walks_len, all_contigs_len = ck['walks'], ck['all_walks_len'], ck['all_contigs_len']
+        if ck['visited']:
+            visited[np.fromiter(ck['visited'], dtype=np.int64, count=len(ck['visited']))] = True
+    while True:
+        # get_subgraph (:40-51): the edges whose endpoints are both unvisited, in the order of their ids
+        remaining = np.nonzero(~visited[src] & ~visited[dst])[0]
+        if remaining.size == 0:                                         # :201-203
+            break
+        idx_edges = sample_edges(prob_all[torch.from_numpy(remaining)], nb_paths, fast_sampling)   # :205-210
+        cands = list(dict.fromkeys((int(src[remaining[i]]), int(dst[remaining[i]])) for i in idx_edges.tolist()))
+        walks, contig_lens = [], []
+        for (s, d), (walk_f, walk_b, _, _) in zip(cands, wg.run_greedy_both_ways(cands, log_probs, visited, threads)):
+            walk = walk_b + walk_f                                      # :257
+            length = wg.get_contig_length(walk, prefix_length, read_length)             # :261
+            if s == d or len(walk) < 2:                                 # :263-264, :282-287: a self-loop counts for nothing
+                length = 0
+            walks.append(walk)
+            contig_lens.append(length)
+        best = contig_lens.index(max(contig_lens))                      # :306-307: first of the longest
+        best_walk = walks[best]
+        if contig_lens[best] < len_threshold:                           # :335-336
+            break
+        visited[best_walk] = True                                       # visited_f | visited_b: the walk and its complements
+        visited[np.asarray(best_walk) ^ 1] = True
+        jumped = wg.jumped_nodes(best_walk)                             # :316-322
+        if jumped:
+            visited[np.fromiter(jumped, dtype=np.int64, count=len(jumped))] = True
+        all_contigs.append(best_walk)
+        all_walks_len.append(len(best_walk))
+        all_contigs_len.append(contig_lens[best])
+        if len(all_contigs) % 10 == 0 and checkpoint_dir is not None:   # :344-359
+            ck = dict(walks=all_contigs, visited=set(np.nonzero(visited)[0].tolist()), all_walks_len=all_walks_len,
+                      all_contigs_len=all_contigs_len)
+            tmp = os.path.join(checkpoint_dir, 'checkpoint_tmp.pkl')
+            with open(tmp, 'wb') as f:
+                pickle.dump(ck, f)
+            os.rename(tmp, ckpt_file)
+    return all_contigs

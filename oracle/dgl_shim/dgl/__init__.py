@@ -167,3 +167,35 @@ def node_subgraph(g, nodes, relabel_nodes=True, store_ids=True):
     if store_ids:
         sub.ndata[NID], sub.edata[EID] = ids.to(g._src.dtype), eids.to(g._src.dtype)
     return sub
+
+
+class _EdgeSpace:
+    """``g.edges[u, v]``: the edges between the node pairs; ``.data[name]`` reads their features (DGL picks ONE edge id
+    per pair through ``edge_ids``; which one, when a pair has several, is unspecified -- callers here use simple graphs)."""
+
+    def __init__(self, g, eids):
+        self.data = {k: v[eids] for k, v in g.edata.items()}
+
+
+class _EdgesView:
+    """``g.edges()`` -> (src, dst) and ``g.edges[u, v]`` -> _EdgeSpace, like DGL's EdgeView."""
+
+    def __init__(self, g):
+        self._g = g
+
+    def __call__(self, form='uv'):
+        return self._g._src, self._g._dst
+
+    def __getitem__(self, key):
+        u, v = key
+        g = self._g
+        if getattr(g, '_pair_eid', None) is None:
+            g._pair_eid = {}
+            for k, (a, b) in enumerate(zip(g._src.tolist(), g._dst.tolist())):
+                g._pair_eid.setdefault((a, b), k)
+        u = u.tolist() if torch.is_tensor(u) else list(u)
+        v = v.tolist() if torch.is_tensor(v) else list(v)
+        return _EdgeSpace(g, torch.tensor([g._pair_eid[(a, b)] for a, b in zip(u, v)], dtype=torch.long))
+
+
+DGLGraph.edges = property(lambda self: _EdgesView(self))

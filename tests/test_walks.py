@@ -89,3 +89,54 @@ def test_walker_long_walks_grow_the_buffer():
     mid = n // 2
     (walk_f, walk_b, _, _), = wg.run_greedy_both_ways([(mid, mid + 2)], logp)
     assert walk_b + walk_f == list(range(0, n, 2))
+
+
+@pytest.mark.parametrize('run', [0, 1])
+def test_get_contigs_greedy_matches_reference_run(golden, run, tmp_path):
+    """The whole decoder loop against a run of the reference's own get_contigs_greedy (oracle/make_golden_contigs.py):
+    same torch seed -> the same start edges are sampled -> the same contigs, walk for walk."""
+    from gnnome_b200.assembly import AssemblyGraph
+    from gnnome_b200.decode import get_contigs_greedy
+    g = golden('contigs')
+    src, dst, n = g['src'], g['dst'], g['num_nodes']
+    succs, preds, edges = {i: [] for i in range(n)}, {i: [] for i in range(n)}, {}
+    for k, (u, v) in enumerate(zip(src.tolist(), dst.tolist())):
+        succs[u].append(v)
+        preds[v].append(u)
+        edges[(u, v)] = k
+    ag = AssemblyGraph(src, dst, n, dict(score=g['score'], prefix_length=g['prefix_length']), dict(read_length=g['read_length']))
+    ref = g['runs'][run]
+    torch.manual_seed(ref['seed'])
+    walks = get_contigs_greedy(ag, succs, preds, edges, ref['len_threshold'], ref['nb_paths'], checkpoint_dir=str(tmp_path))
+    assert walks == ref['walks']
+    if len(walks) >= 10:                       # a checkpoint was written after the 10th contig, in the reference's format
+        import pickle
+        ck = pickle.load(open(tmp_path / 'checkpoint.pkl', 'rb'))
+        assert ck['walks'][:10] == ref['walks'][:10] and set(ck) == {'walks', 'visited', 'all_walks_len', 'all_contigs_len'}
+        # resuming from it finishes with the same contigs when the remaining draws are replayed... the RNG state is
+        # not part of the reference's checkpoint, so only the restored prefix is checked
+        resumed = get_contigs_greedy(ag, succs, preds, edges, 10 ** 12, ref['nb_paths'], checkpoint_dir=str(tmp_path),
+                                     load_checkpoint=True)
+        assert resumed == ck['walks']           # threshold too high for anything new: the restored walks come back
+
+
+def test_get_contigs_greedy_with_labels(golden):
+    from gnnome_b200.assembly import AssemblyGraph
+    from gnnome_b200.decode import get_contigs_greedy
+    g = golden('contigs')
+    n = g['num_nodes']
+    src, dst = g['src'][:400], g['dst'][:400]
+    succs, preds, edges = {}, {}, {}
+    for k, (u, v) in enumerate(zip(src.tolist(), dst.tolist())):
+        succs.setdefault(u, []).append(v)
+        preds.setdefault(v, []).append(u)
+        edges[(u, v)] = k
+    y = (torch.arange(400) % 3 != 0).float()
+    ag = AssemblyGraph(src, dst, n, dict(y=y, prefix_length=g['prefix_length'][:400]), dict(read_length=g['read_length']))
+    torch.manual_seed(1)
+    for fast in (False, True):
+        walks = get_contigs_greedy(ag, succs, preds, edges, 0, nb_paths=8, use_labels=True, fast_sampling=fast)
+        assert walks and all(len(w) >= 2 for w in walks)
+        used = [v for w in walks for v in w]
+        assert len(used) == len(set(used))          # a node is used by at most one contig
+        assert not ({v ^ 1 for v in used} & set(used))   # ... and never together with its reverse complement
