@@ -243,7 +243,8 @@ class AssemblyGraphDataset:
     """graph_dataset.py:46-56 without DGL: every ``{root}/{assembler}/processed/{idx}.pt`` (``AssemblyGraph.save``
     files) is loaded, preprocessed and given its degrees; iteration yields ``(idx, graph)`` in index order."""
 
-    def __init__(self, root, assembler, device=None):
+    def __init__(self, root, assembler, device=None, preprocess=True):
+        """``preprocess=False`` only loads the graphs (no device work): enough when ``{idx}_predicts.pt`` already exist."""
         self.root = os.path.abspath(root)
         self.assembler = assembler
         self.assembly_dir = os.path.join(self.root, assembler)
@@ -255,7 +256,8 @@ class AssemblyGraphDataset:
             if ext != '.pt' or not stem.isdigit():
                 continue
             g = AssemblyGraph.load(os.path.join(self.save_dir, name))
-            g = add_positional_encoding(preprocess_graph(g, device=device), device=device)
+            if preprocess:
+                g = add_positional_encoding(preprocess_graph(g, device=device), device=device)
             self.graph_list.append((int(stem), g))
         self.graph_list.sort(key=lambda t: t[0])
 

@@ -140,3 +140,40 @@ def test_get_contigs_greedy_with_labels(golden):
         used = [v for w in walks for v in w]
         assert len(used) == len(set(used))          # a node is used by at most one contig
         assert not ({v ^ 1 for v in used} & set(used))   # ... and never together with its reverse complement
+
+
+def test_inference_driver_from_existing_predictions(golden, tmp_path):
+    """gnnome_b200.inference.inference on a dataset directory laid out like the reference's: with {idx}_predicts.pt in
+    place (inference.py:429-431) no device is needed; walks are pickled like the reference's and equal a direct decode."""
+    import pickle
+    from gnnome_b200.assembly import AssemblyGraph
+    from gnnome_b200.decode import get_contigs_greedy
+    from gnnome_b200.inference import inference
+    g = golden('contigs')
+    src, dst, n = g['src'], g['dst'], g['num_nodes']
+    succs, preds, edges = {i: [] for i in range(n)}, {i: [] for i in range(n)}, {}
+    for k, (u, v) in enumerate(zip(src.tolist(), dst.tolist())):
+        succs[u].append(v)
+        preds[v].append(u)
+        edges[(u, v)] = k
+    data, save = tmp_path / 'data', tmp_path / 'out'
+    (data / 'hifiasm' / 'processed').mkdir(parents=True)
+    (data / 'hifiasm' / 'info').mkdir()
+    prefix = g['prefix_length'].clone()
+    prefix[:5] = -3                                   # negative prefixes are clamped to 0 before decoding (inference.py:461)
+    AssemblyGraph(src, dst, n, dict(prefix_length=prefix, overlap_length=g['prefix_length'],
+                                    overlap_similarity=torch.ones(src.numel())), dict(read_length=g['read_length'])
+                  ).save(data / 'hifiasm' / 'processed' / '0.pt')
+    for name, obj in (('succ', succs), ('pred', preds), ('edges', edges)):
+        pickle.dump(obj, open(data / 'hifiasm' / 'info' / f'0_{name}.pkl', 'wb'))
+    (save / 'decode').mkdir(parents=True)
+    torch.save(g['score'], save / 'decode' / '0_predicts.pt')
+    hp = dict(num_decoding_paths=20, len_threshold=60_000, seed=5, load_checkpoint=False)
+    out = inference(str(data), 'no-model-needed.pt', 'hifiasm', str(save), hyperparameters=hp)
+    walks = pickle.load(open(save / 'decode' / '0_walks.pkl', 'rb'))
+    assert out == {0: walks} and len(walks) >= 3
+    ag = AssemblyGraph(src, dst, n, dict(score=g['score'], prefix_length=prefix.clamp_min(0)), dict(read_length=g['read_length']))
+    torch.manual_seed(5)
+    assert walks == get_contigs_greedy(ag, succs, preds, edges, 60_000, 20)
+    with pytest.raises(ValueError, match='strategy'):
+        inference(str(data), 'x', 'hifiasm', str(save), hyperparameters=dict(strategy='beam'))
