@@ -177,3 +177,39 @@ def test_inference_driver_from_existing_predictions(golden, tmp_path):
     assert walks == get_contigs_greedy(ag, succs, preds, edges, 60_000, 20)
     with pytest.raises(ValueError, match='strategy'):
         inference(str(data), 'x', 'hifiasm', str(save), hyperparameters=dict(strategy='beam'))
+
+
+def test_walker_vs_oracle_random_graphs_with_ties_and_multi_edges():
+    """Property test on small random graphs (self-loops, duplicate pairs, dead ends, exact score ties, random visited
+    sets): the C++ walker against the oracle's pure-Python restatement -- walks, float32 sums, contig lengths, jumped-over
+    nodes."""
+    from hypothesis import given, settings, strategies as st
+    from gnnome_b200.decode import WalkGraph
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(2, 12), st.integers(0, 60), st.integers(0, 2 ** 31 - 1))
+    def check(half_nodes, m, seed):
+        n = 2 * half_nodes
+        rng = np.random.default_rng(seed)
+        src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+        succs, preds, edges = {i: [] for i in range(n)}, {i: [] for i in range(n)}, {}
+        for k, (u, v) in enumerate(zip(src.tolist(), dst.tolist())):
+            succs[u].append(v)
+            preds[v].append(u)
+            edges[(u, v)] = k
+        log_probs = torch.log(torch.from_numpy(rng.choice([0.1, 0.5, 0.5, 0.9], max(m, 1)).astype(np.float32)))
+        visited = set(np.nonzero(np.repeat(rng.random(half_nodes) < 0.3, 2))[0].tolist())
+        prefix, reads = torch.from_numpy(rng.integers(0, 50, max(m, 1))), torch.from_numpy(rng.integers(1, 90, n))
+        wg = WalkGraph.from_edge_list(src, dst, n)
+        assert all(np.array_equal(a, b) for a, b in zip(wg._succ, WalkGraph.from_dicts(n, succs, edges, preds)._succ))
+        cands = [(int(src[k]), int(dst[k])) for k in range(min(m, 6))]
+        for (s, d), (walk_f, walk_b, sum_f, sum_b) in zip(cands, wg.run_greedy_both_ways(cands, log_probs, visited, threads=2)):
+            rf, rb, rsf, rsb = R.run_greedy_both_ways(s, d, log_probs, succs, edges, visited)
+            assert (walk_f, walk_b) == (rf, rb)
+            assert np.float32(sum_f) == rsf.numpy()[0] and np.float32(sum_b) == rsb.numpy()[0]
+            walk = walk_b + walk_f
+            if all((u, v) in edges for u, v in zip(walk[:-1], walk[1:])):
+                assert wg.get_contig_length(walk, prefix, reads) == R.contig_length(walk, edges, prefix, reads)
+            assert wg.jumped_nodes(walk) == R.jumped_nodes(walk, succs, preds)
+
+    check()
