@@ -26,19 +26,30 @@ def _np(t, dtype):
 
 
 def _csr_from_dicts(num_nodes, lists, edge_of=None):
-    counts = np.zeros(num_nodes, dtype=np.int64)
-    for i, nbrs in lists.items():
-        counts[i] = len(nbrs)
+    """CSR of ``lists`` (node -> list of neighbours, list order kept) and, with ``edge_of`` ((u, v) -> id), the edge id
+    of every entry.  The pair look-up is a sort + binary search over the dict's keys instead of one dict access per
+    entry (60 M of them on a 10 M-node graph)."""
+    from itertools import chain
+    empty = ()
+    counts = np.fromiter((len(lists.get(i, empty)) for i in range(num_nodes)), dtype=np.int64, count=num_nodes)
     ptr = np.zeros(num_nodes + 1, dtype=np.int64)
     np.cumsum(counts, out=ptr[1:])
-    node = np.empty(int(ptr[-1]), dtype=np.int32)
-    edge = np.zeros(int(ptr[-1]), dtype=np.int32)
-    for i, nbrs in lists.items():
-        if len(nbrs):
-            node[ptr[i]:ptr[i + 1]] = nbrs
-            if edge_of is not None:
-                edge[ptr[i]:ptr[i + 1]] = [edge_of[(i, int(v))] for v in nbrs]
-    return ptr, node, edge
+    total = int(ptr[-1])
+    node = np.fromiter(chain.from_iterable(lists.get(i, empty) for i in range(num_nodes)), dtype=np.int64, count=total)
+    edge = np.zeros(total, dtype=np.int32)
+    if edge_of is not None and total:
+        m = len(edge_of)
+        keys = np.fromiter(chain.from_iterable(edge_of.keys()), dtype=np.int64, count=2 * m).reshape(m, 2)
+        vals = np.fromiter(edge_of.values(), dtype=np.int64, count=m)
+        flat = keys[:, 0] * num_nodes + keys[:, 1]
+        order = np.argsort(flat, kind='stable')
+        want = np.repeat(np.arange(num_nodes, dtype=np.int64), counts) * num_nodes + node
+        pos = np.searchsorted(flat[order], want)
+        if (pos >= m).any() or (flat[order][np.minimum(pos, m - 1)] != want).any():
+            bad = int(np.nonzero((pos >= m) | (flat[order][np.minimum(pos, m - 1)] != want))[0][0])
+            raise KeyError((int(want[bad] // num_nodes), int(want[bad] % num_nodes)))
+        edge = vals[order][pos].astype(np.int32)
+    return ptr, node.astype(np.int32), edge
 
 
 def _csr_from_edges(key_nodes, other_nodes, eids, num_nodes):
