@@ -49,3 +49,9 @@ def test_no_cpu_fallback():
     model = gnnome_b200.models.SymGatedGCNModel(2, 2, 64, 16, 2, 64, 'batch').eval()
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         model((torch.tensor([0]), torch.tensor([0]), 1), torch.zeros(1, 2), torch.zeros(1, 2))
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md section 2 maps every C-ABI symbol to the reference lines it replaces."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    assert [n for n in _declared() if f'`{n}`' not in doc] == []
