@@ -78,6 +78,7 @@ class HaloPlan:
         self.world, self.group = shard.world, group
         self.recv_counts = list(shard.recv_counts)
         world = shard.world
+        self.active = False          # does ANY rank exchange rows?  (a collective has to be entered by every rank)
         if world == 1:
             self.send_counts = [0]
             self.send_idx = torch.zeros(0, dtype=torch.int32, device=device)
@@ -93,6 +94,9 @@ class HaloPlan:
         if asked.numel() and (int(asked.min()) < shard.lo or int(asked.max()) >= shard.hi):
             raise RuntimeError('halo plan: a peer asked for a node this rank does not own')
         self.send_idx = (asked - shard.lo).to(torch.int32).contiguous()
+        busy = torch.tensor([int(shard.n_halo > 0 or asked.numel() > 0)], dtype=torch.int64, device=device)
+        dist.all_reduce(busy, op=dist.ReduceOp.MAX, group=group)
+        self.active = bool(busy.item())
         # reverse exchange: rows arrive in send_idx order; group them per owned node (stable => rank order)
         order = torch.argsort(self.send_idx.long(), stable=True)
         self.xp_row = order.to(torch.int32).contiguous()
@@ -276,13 +280,13 @@ class ShardedForward:
             flags = conv._flags()
             carry = self._buf('carry', k.carry_shape(gi, H))
             k.node_linear_layer(pk, h, nb * H, P[:n_own])
-            if n_halo or plan.n_send:                                        # exchange (1)
+            if plan.active:                                        # exchange (1)
                 out_rows = k.gather_rows(P[:n_own, :2 * H], plan.send_idx, self._buf('s1', (plan.n_send, 2 * H)))
                 halo = plan.to_consumers(out_rows, self._buf('r1', (n_halo, 2 * H)))
                 P[n_own:, :2 * H].copy_(halo)
             k.edge_forward(gi, H, P, pk, e_pos, Fb, carry, flags)
             xp_buf = None
-            if self.sym and (n_halo or plan.n_send):                         # exchange (2)
+            if self.sym and plan.active:                         # exchange (2)
                 part = self._buf('s2', (n_halo, 2 * H))
                 k.reverse_partial(gi, H, P, e_pos, n_own, n_local, part)
                 xp_buf = plan.to_owners(part, self._buf('r2', (plan.n_send, 2 * H)))
@@ -294,7 +298,7 @@ class ShardedForward:
         hs = S_own.shape[1] // 2
         S = self._buf('S', (n_local, 2 * hs))
         S[:n_own].copy_(S_own)
-        if n_halo or plan.n_send:
+        if plan.active:
             out_rows = k.gather_rows(S_own[:, :hs], plan.send_idx, self._buf('s3', (plan.n_send, hs)))
             S[n_own:, :hs].copy_(plan.to_consumers(out_rows, self._buf('r3', (n_halo, hs))))
         scores = torch.empty((sh.num_edges, 1), dtype=self.dtype, device=self.device)

@@ -78,6 +78,45 @@ def test_sharded_forward_matches_oracle_gloo(tmp_path, world, kind, p_long):
     assert all(s[1] > 0 for s in res['sizes'])           # every rank really had a halo to exchange
 
 
+def _degenerate_worker(rank, world, port, out_path):
+    import gnnome_b200
+    from _emul import EmulKernels
+    from oracle import restatement as R
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        # every edge but one enters node 5: ranks 1 and 2 own no node and no edge, rank 3 owns one edge and has no halo
+        src = torch.tensor([0, 1, 2, 3, 6, 6], dtype=torch.int32)
+        dst = torch.tensor([5, 5, 5, 5, 5, 7], dtype=torch.int32)
+        n, m = 8, 6
+        x, e = torch.randn(n, 2), torch.randn(m, 2)
+        model = gnnome_b200.models.SymGatedGCNModel(2, 2, 32, 16, 2, 64, 'batch').eval()
+        runner = partition.ShardedForward(model, src, dst, n, x, e, rank, world, torch.device('cpu'),
+                                          kernels=EmulKernels(torch.float64), dtype=torch.float64)
+        with torch.no_grad():
+            full = partition.gather_scores(runner, runner.step(), m)
+        sizes = [None] * world
+        dist.all_gather_object(sizes, (runner.shard.n_own, runner.shard.n_halo, runner.shard.num_edges))
+        if rank == 0:
+            ref = R.model_forward({k: v.clone() for k, v in model.state_dict().items()}, src, dst, n, x, e,
+                                  dtype=torch.float64, faithful=False)
+            torch.save({'err': (full.double() - ref).abs().max().item(), 'sizes': sizes}, out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_ranks_without_work_still_enter_the_exchanges(tmp_path):
+    """A rank that owns nothing (and one without a halo) must still take part in every all_to_all: the exchanges are
+    collectives.  (They used to be guarded by the rank's own counts, which dead-locked this case.)"""
+    out = str(tmp_path / 'res.pt')
+    mp.spawn(_degenerate_worker, args=(4, _free_port(), out), nprocs=4, join=True)
+    res = torch.load(out)
+    assert res['err'] < 1e-12, res
+    assert [s[2] for s in res['sizes']] == [5, 0, 0, 1] and res['sizes'][1][0] == 0
+
+
 def test_node_bounds_balance_in_edges():
     src, dst, _, _ = _inputs(2000, 12000, 1, 0.01)
     b = partition.node_bounds(dst, 2000, 4)
