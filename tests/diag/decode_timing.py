@@ -1,5 +1,5 @@
 """Wall time of a whole greedy decode (get_contigs_greedy) on a seeded synthetic graph: gnnome_b200.decode against the
-reference's own function (build container only).  Usage: python tools/decode_timing.py [N E nb_paths]"""
+reference's own function (build container only).  Usage: python tests/diag/decode_timing.py [N E nb_paths]"""
 import contextlib
 import io
 import os
@@ -8,7 +8,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import make_golden_contigs as M  # noqa: E402  (timing baseline only)
 from oracle import reference_runner as rr  # noqa: E402

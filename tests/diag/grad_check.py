@@ -1,13 +1,13 @@
 """Gradient accuracy of the training path against an fp64 evaluation of the oracle restatement (CPU), next to the
 accuracy of the reference's own fp32 gradients (the fixture).  Prints, per parameter, max |g - g64| / max |g64|.
-Usage: python tools/grad_check.py [bce|sym]"""
+Usage: python tests/diag/grad_check.py [bce|sym]"""
 import os
 import sys
 
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import restatement as R  # noqa: E402  (checker only)
 import gnnome_b200  # noqa: E402

@@ -6,7 +6,7 @@ import sys
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import gnnome_b200  # noqa: E402
 from gnnome_b200 import assembly as A  # noqa: E402

@@ -1,7 +1,7 @@
 """GPU bring-up of the split16 / TMA kernels: each stage against a torch reference, errors printed (not asserted)."""
 import sys, os, traceback
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import gnnome_b200
 from gnnome_b200 import ops, synth
 from oracle import restatement as R
@@ -101,7 +101,7 @@ def t_layer():
 
 
 def t_model():
-    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'weights.pt'), weights_only=True)
+    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'golden', 'weights.pt'), weights_only=True)
     for H, L, n, m in [(64, 8, 20000, 120000), (128, 4, 10000, 60000), (256, 3, 6000, 36000), (256, 8, 100000, 600000)]:
         s, d = synth.make_assembly_graph(n, m, seed=H)
         x, e = synth.make_features(s, d, n, seed=H)
@@ -126,7 +126,7 @@ def t_model():
 def t_determinism():
     """Each kernel twice on identical inputs (H=64 shipped weights, 300k edges): bitwise equal?"""
     from gnnome_b200.layers.encoders import encode_rows2
-    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'weights.pt'), weights_only=True)
+    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'golden', 'weights.pt'), weights_only=True)
     for H, n, m in [(64, 50000, 300000), (128, 50000, 300000), (256, 50000, 300002)]:
         s, d = synth.make_assembly_graph(n, m, seed=5)
         x, e = synth.make_features(s, d, n, seed=5)
@@ -195,7 +195,7 @@ def t_determinism():
 def t_layers():
     """Two full passes layer by layer (H=64 shipped weights, 300k edges): first tensor that differs."""
     from gnnome_b200.layers.encoders import encode_rows2
-    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'weights.pt'), weights_only=True)
+    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'golden', 'weights.pt'), weights_only=True)
     H, n, m = 64, 50000, 300000
     s, d = synth.make_assembly_graph(n, m, seed=5)
     x, e = synth.make_features(s, d, n, seed=5)
@@ -242,7 +242,7 @@ def t_layers():
 def t_badrow():
     """Layer 0 of the H=64 shipped model at 300k edges, workspace pre-filled with NaN: dump the rows that are off."""
     from gnnome_b200.layers.encoders import encode_rows2
-    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'weights.pt'), weights_only=True)
+    sd = torch.load(os.path.join(os.path.dirname(__file__), '..', 'golden', 'weights.pt'), weights_only=True)
     H, n, m = 64, 50000, 300000
     s, d = synth.make_assembly_graph(n, m, seed=5)
     x, e = synth.make_features(s, d, n, seed=5)

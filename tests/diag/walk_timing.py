@@ -1,6 +1,6 @@
 """Time of one decoder iteration's candidate walks (100 start edges, nothing visited yet): the C++ walker against the
 reference's own Python functions (build container only: they are read from /root/reference through
-oracle/reference_runner.py) and against the oracle restatement.  Usage: python tools/walk_timing.py [N E]"""
+oracle/reference_runner.py) and against the oracle restatement.  Usage: python tests/diag/walk_timing.py [N E]"""
 import math
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from gnnome_b200 import synth  # noqa: E402
 from gnnome_b200.decode import WalkGraph  # noqa: E402

@@ -155,7 +155,7 @@ def test_training_losses_vs_reference_functions(gnb, golden, shipped_weights, ki
     assert abs(loss.item() - ref['loss'].item()) <= 1e-5 * max(1.0, abs(ref['loss'].item()))
     # Gradients.  The network has ~2 M ReLU inputs per forward and a handful of them sit within fp32 noise of zero; when
     # an fp32 evaluation lands on the other side of such a kink than the reference's did, it returns a different (equally
-    # valid) subgradient.  On this fixture one flipped element of layer 1 (|ehat| = 3e-7, tools/grad_dump_gate.py)
+    # valid) subgradient.  On this fixture one flipped element of layer 1 (|ehat| = 3e-7, tests/diag/grad_dump_gate.py)
     # moves the first layers' gradients by 1e-3 .. 6e-2 of their scale although every kernel reproduces its own inputs
     # to 1e-7.  So: the strict per-parameter bound holds for the single-forward case (no flip on that fixture); with two
     # forwards the per-parameter bound is loose and the overall direction is checked in the L2 norm.
