@@ -290,6 +290,8 @@ class ShardedForward:
                 part = self._buf('s2', (n_halo, 2 * H))
                 k.reverse_partial(gi, H, P, e_pos, n_own, n_local, part)
                 xp_buf = plan.to_owners(part, self._buf('r2', (plan.n_send, 2 * H)))
+            if plan.n_send == 0:                                             # took part in the exchange, received nothing
+                xp_buf = None
             h = k.node_update(gi, H, P, pk, e_pos, Fb, carry, h, flags, n_own,
                               plan.xp_ptr if xp_buf is not None else None,
                               plan.xp_row if xp_buf is not None else None, xp_buf)
