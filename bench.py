@@ -76,6 +76,55 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
+STEP_BUDGET_S = float(os.environ.get('GNB_BENCH_STEP_BUDGET_S', 30))   # host-side watchdog: seconds allowed per step
+
+
+def error_line(args, what):
+    """The JSON line of a run that did not finish: the driver learns WHY instead of timing out on silence."""
+    hang = ''
+    try:
+        from gnnome_b200 import _lib
+        hang = _lib.hang_report()
+    except Exception:   # noqa: BLE001
+        pass
+    return {'metric': 'edges/s', 'value': None, 'unit': 'edges/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'error': what, 'hang_report': hang or None,
+            'config': {'workload': WORKLOADS[args.workload][4]}}
+
+
+class Watchdog:
+    """A device hang must not be a silent 30-minute burn: every phase of the run is armed with a wall-clock budget
+    (STEP_BUDGET_S per step); when it expires -- the main thread is then stuck in a synchronize -- rank 0 prints a
+    JSON line carrying "error" (and the kernels' own spin-watchdog record, if one fired) and the process exits.
+    The device-side watchdog (gnb_hang_report) normally fires first, as a CUDA error that main() reports."""
+
+    def __init__(self, args, rank):
+        self.args, self.rank, self.deadline, self.label = args, rank, None, ''
+        self.lock = threading.Lock()
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def arm(self, label, steps):
+        with self.lock:
+            self.label, self.deadline = label, time.time() + 60.0 + STEP_BUDGET_S * steps
+
+    def disarm(self):
+        with self.lock:
+            self.deadline = None
+
+    def _run(self):
+        while True:
+            time.sleep(0.5)
+            with self.lock:
+                expired = self.deadline is not None and time.time() > self.deadline
+                label = self.label
+            if expired:
+                log(f'[bench] watchdog: phase {label!r} exceeded its budget')
+                if self.rank == 0:
+                    emit(error_line(self.args, f'phase {label!r} exceeded its wall-clock budget '
+                                               f'({STEP_BUDGET_S:.0f} s per step): device hang'))
+                os._exit(3)
+
+
 def dist_env():
     return int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 
@@ -239,6 +288,7 @@ def run_gpu_arm(args, wl):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=device)
 
+    dog = Watchdog(args, rank)
     model = make_model(H, L, device)
     src, dst, x, e = make_inputs(n, m, seed=0)
 
@@ -262,9 +312,11 @@ def run_gpu_arm(args, wl):
     else:
         step = runner.step
     with torch.no_grad():
+        dog.arm('warm-up', args.warmup)
         for _ in range(args.warmup):
             out = step()
         barrier()
+        dog.arm('timed steps', args.steps)
         ops.LaunchLog.reset(enabled=True, timing=True)
         sampler = ClockSampler(local_rank) if rank == 0 else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -274,6 +326,7 @@ def run_gpu_arm(args, wl):
         ev1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
+    dog.disarm()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = ops.LaunchLog.total()
     ktimes = ops.LaunchLog.times_ms()
@@ -304,6 +357,7 @@ def run_gpu_arm(args, wl):
 
     # ---- end-to-end through the public call with pinned host buffers ---------------------------
     e2e = None
+    dog.arm('end-to-end steps', 2 * (1 + max(1, min(args.steps, 3))))
     if runner is None:
         hs, hd, hx, he = (t.pin_memory() for t in (src, dst, x, e))
         e2e_steps = max(1, min(args.steps, 3))
@@ -347,10 +401,12 @@ def run_gpu_arm(args, wl):
                'includes': 'per rank: H2D of its shard (local src/dst, x, e), graph staging, forward with halo '
                            'exchanges, D2H of its scores; max over ranks'}
 
+    dog.arm('teardown', 2)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+    dog.disarm()
     if rank != 0:
         return
     # ---- CPU baseline + parity on the bounded sample (rank 0, N=1 only) ------------------------
@@ -361,8 +417,11 @@ def run_gpu_arm(args, wl):
         sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         r = cpu_oracle_run(sd, H, L, steps=CPU_PASSES, warmup=1)    # ~3 s per pass at H=256: 10-15 s of CPU work
         s_src, s_dst, s_x, s_e = r['inputs']
+        dog.arm('parity sample', 2)
         with torch.no_grad():
             ours = model((s_src, s_dst, r['n']), s_x, s_e)
+        torch.cuda.synchronize()
+        dog.disarm()
         perr = (torch.sigmoid(ours.double().cpu()) - torch.sigmoid(r['out'].double())).abs().max().item()
         t_cpu = float(np.mean(r['times']))
         cpu = {'value': r['m'] / t_cpu, 'unit': 'edges/s', 'cores': r['cores'], 'kind': 'port',
@@ -397,8 +456,15 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
         run_reference_arm(args, wl)
-    else:
+        return
+    try:
         run_gpu_arm(args, wl)
+    except Exception as exc:   # noqa: BLE001 -- a CUDA error (e.g. the kernels' spin watchdog trapped): say so in the line
+        import traceback
+        traceback.print_exc()
+        if dist_env()[0] == 0:
+            emit(error_line(args, f'{type(exc).__name__}: {exc}'[:2000]))
+        os._exit(3)
 
 
 if __name__ == '__main__':

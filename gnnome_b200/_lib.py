@@ -43,14 +43,12 @@ SIGNATURES = {
     'gnb_node_linear': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
     'gnb_packed_linear_bytes': (_S, [_I, _I]),
     'gnb_pack_linear_tc': (_I, [_P, _I, _I, _P, _P]),
-    'gnb_node_linear_tc': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
+    'gnb_set_spin_timeout_ms': (None, [ctypes.c_longlong]),
+    'gnb_hang_report': (_I, [ctypes.c_char_p, _S]),
     'gnb_edge_chunk': (_I, [_I]),
     'gnb_edge_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P]),
     'gnb_node_update': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),
     'gnb_reverse_partial': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _L, _L, _P, _P]),
-    'gnb_edge_chunk_tc': (_I, [_I]),
-    'gnb_edge_tile_tc': (_I, [_I]),
-    'gnb_edge_forward_tc': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     'gnb_score_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'gnb_split16_bytes': (_S, [_L, _I]),
     'gnb_split_rows': (_I, [_P, _P, _L, _I, _P, _P]),
@@ -58,8 +56,10 @@ SIGNATURES = {
     'gnb_encode2': (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'gnb_node_linear_tc2': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
     'gnb_edge_tile_tc2': (_I, [_I]),
-    'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    'gnb_edge_chunk_tc2': (_I, [_I]),
+    'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P]),
     'gnb_debug_edge_timing': (None, [_P]),
+    'gnb_debug_store_delay_ns': (None, [_I]),
     'gnb_node_update2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),
     'gnb_reverse_partial2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _L, _L, _P, _P]),
     'gnb_score_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -90,7 +90,7 @@ SIGNATURES = {
     'gnb_walk_jumped_nodes': (_I, [ctypes.POINTER(GnbWalkGraph), ctypes.POINTER(GnbWalkGraph), _P, _L, _P]),
 }
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 
@@ -116,7 +116,15 @@ def load():
     return lib
 
 
+def hang_report():
+    """The spin watchdog's record of a device-side wait that timed out in this process ('' if none):
+    which kernel / block / warp role waited for which barrier.  Readable after the CUDA context has died."""
+    buf = ctypes.create_string_buffer(512)
+    return buf.value.decode() if load().gnb_hang_report(buf, len(buf)) else ''
+
+
 def check(rc, what):
     if rc != 0:
         msg = load().gnb_last_error()
-        raise RuntimeError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')
+        hang = hang_report()
+        raise RuntimeError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}' + (f' [{hang}]' if hang else ''))

@@ -37,18 +37,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
 // non-blocking test: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -63,22 +51,73 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Same, for waits that are expected to take long (a whole pipeline stage): back off between polls so that the
-// spinning warp does not take issue slots from the warps doing the work on the same scheduler.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!done) __nanosleep(ns);
-  } while (!done);
+
+// ---------------------------------------------------------------------------------------------
+// Spin watchdog.  Every device-side wait of the tensor-core kernels is bounded: a wait that lasts longer than
+// Watch::timeout_ns (wall clock, %globaltimer) writes WHO waited for WHAT into a record in host-mapped memory and
+// traps, so that a lost barrier phase surfaces as a CUDA error with a diagnosis (gnb_hang_report) within seconds
+// instead of a silent spin.  The clock is read once every 256 polls of a wait that has not succeeded at once.
+// ---------------------------------------------------------------------------------------------
+struct Watch {
+  unsigned long long* rec;         // kWatchWords words in cudaHostAllocMapped memory, or nullptr
+  unsigned long long timeout_ns;   // 0 = wait for ever
+};
+constexpr int kWatchWords = 8;
+constexpr unsigned long long kWatchMagic = 0x474e42484e47ull;   // "GNBHNG"
+enum WatchKernel : uint32_t { kWkEdge2 = 1, kWkLinear2 = 2, kWkScore2 = 3 };
+enum WatchRole : uint32_t { kWrProducer = 1, kWrMma = 2, kWrStore = 3, kWrEpilogue = 4 };
+enum WatchBar : uint32_t { kWbFull = 1, kWbEmpty = 2, kWbDFull = 3, kWbDEmpty = 4, kWbSFull = 5 };
+__host__ __device__ constexpr uint32_t watch_tag(uint32_t kernel, uint32_t role, uint32_t bar) {
+  return (kernel << 16) | (role << 8) | bar;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+static __device__ __noinline__ void watch_fail(Watch w, uint32_t tag, uint32_t index, uint32_t parity, long long iter,
+                                        unsigned long long waited_ns) {
+  if (w.rec != nullptr) {
+    volatile unsigned long long* r = w.rec;
+    r[1] = tag;
+    r[2] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+    r[3] = ((unsigned long long)index << 32) | parity;
+    r[4] = (unsigned long long)iter;
+    r[5] = waited_ns;
+    __threadfence_system();
+    r[0] = kWatchMagic;
+    __threadfence_system();
+  }
+  __trap();
+}
+
+// State of one bounded wait (a few registers, live only while a wait is unsuccessful).
+struct SpinGuard {
+  uint32_t polls = 0;
+  unsigned long long t0 = 0;
+  __device__ __forceinline__ void poll(const Watch& w, uint32_t tag, uint32_t index, uint32_t parity, long long iter) {
+    if (((++polls) & 0xffu) == 0 && w.timeout_ns != 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > w.timeout_ns) watch_fail(w, tag, index, parity, iter, now - t0);
+    }
+  }
+};
+
+// Wait for the phase with this parity; `ns` > 0 backs off between polls so that a warp that is expected to wait
+// for a whole pipeline stage does not take issue slots from the warps doing the work on the same scheduler.
+// tag / index / iter only describe the wait for the watchdog record.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t ns, const Watch& w, uint32_t tag,
+                                          uint32_t index, long long iter) {
+  if (mbar_test(bar, parity)) return;
+  SpinGuard g;
+  for (;;) {
+    if (ns != 0) __nanosleep(ns);
+    if (mbar_test(bar, parity)) return;
+    g.poll(w, tag, index, parity, iter);
+  }
 }
 // One lane of a fully converged warp.  Unlike `lane == 0` the compiler knows that exactly one thread is active in
 // the guarded region, so operands of the warp-level instructions issued there (tcgen05.mma, TMA) move to uniform

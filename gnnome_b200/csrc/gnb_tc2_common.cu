@@ -1,10 +1,48 @@
-// split16 state format helpers: tensor maps, fp32 <-> (hi, lo) fp16 image conversion (see gnb_tma.cuh).
+// Shared host / device pieces of the tensor-core kernels: the spin watchdog record, tensor maps, weight packing and
+// the split16 state format (fp32 <-> (hi, lo) fp16 image conversion, see gnb_tma.cuh).
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 #include "gnb_tma.cuh"
 
 namespace gnb {
 namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// spin watchdog (device side: gnb_tc.cuh)
+// ---------------------------------------------------------------------------------------------
+static std::mutex g_watch_mutex;
+static unsigned long long* g_watch_rec = nullptr;     // host-mapped, kWatchWords words
+static bool g_watch_tried = false;
+static long long g_watch_timeout_ms = -1;             // -1: not initialised (GNB_SPIN_TIMEOUT_MS or 10 s)
+
+Watch watch_get() {
+  std::lock_guard<std::mutex> lock(g_watch_mutex);
+  if (g_watch_timeout_ms < 0) {
+    const char* env = getenv("GNB_SPIN_TIMEOUT_MS");
+    g_watch_timeout_ms = (env != nullptr && *env) ? atoll(env) : 10000;
+    if (g_watch_timeout_ms < 0) g_watch_timeout_ms = 0;
+  }
+  if (!g_watch_tried) {
+    g_watch_tried = true;
+    void* p = nullptr;
+    // survives the sticky error a trap leaves behind: the host reads it through its own pointer
+    if (cudaHostAlloc(&p, kWatchWords * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) ==
+        cudaSuccess) {
+      memset(p, 0, kWatchWords * sizeof(unsigned long long));
+      g_watch_rec = (unsigned long long*)p;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  Watch w;
+  w.rec = g_watch_rec;   // unified addressing: the host pointer of mapped memory is valid on the device
+  w.timeout_ns = (unsigned long long)g_watch_timeout_ms * 1000000ull;
+  return w;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -44,6 +82,21 @@ int make_state_map(CUtensorMap* map, const void* base, int64_t rows, int K, int 
     return GNB_E_INVALID;
   }
   return 0;
+}
+
+// W[M][K] fp32 (nn.Linear layout) -> Wp[ceil(M/128)][2][128][K] fp16: (hi, lo) images of 16 * W, zero padded
+__global__ void pack_linear_tc_kernel(const float* __restrict__ W, int M, int K, __half* __restrict__ Wp, int nblk) {
+  const int64_t total = (int64_t)nblk * kM * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int64_t row = i / K;
+    const int blk = (int)(row / kM), r = (int)(row % kM);
+    const float w = (row < M) ? W[row * K + k] * kWScale : 0.f;
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    Wp[((size_t)(blk * 2 + 0) * kM + r) * K + k] = hi;
+    Wp[((size_t)(blk * 2 + 1) * kM + r) * K + k] = lo;
+  }
 }
 
 // out16[r][:] = split(in[idx ? idx[r] : r][:]); one thread per 8 consecutive channels
@@ -95,6 +148,46 @@ __global__ void merge_rows_kernel(const __half* __restrict__ in, const int32_t* 
 }  // namespace gnb
 
 using namespace gnb;
+
+extern "C" void gnb_set_spin_timeout_ms(long long ms) {
+  std::lock_guard<std::mutex> lock(tc::g_watch_mutex);
+  tc::g_watch_timeout_ms = ms < 0 ? 0 : ms;
+}
+
+extern "C" int gnb_hang_report(char* buf, size_t cap) {
+  static const char* kKernel[] = {"?", "gnb_edge_forward_tc2", "gnb_node_linear_tc2", "gnb_score_forward_tc2"};
+  static const char* kRole[] = {"?", "producer", "mma", "store", "epilogue"};
+  static const char* kBar[] = {"?", "full", "empty", "dfull", "dempty", "sfull"};
+  const volatile unsigned long long* r = tc::g_watch_rec;
+  if (r == nullptr || r[0] != tc::kWatchMagic) {
+    if (buf != nullptr && cap > 0) buf[0] = 0;
+    return 0;
+  }
+  const unsigned tag = (unsigned)r[1];
+  const unsigned k = (tag >> 16) & 0xff, role = (tag >> 8) & 0xff, bar = tag & 0xff;
+  if (buf != nullptr && cap > 0)
+    snprintf(buf, cap,
+             "device spin timed out: kernel %s, block %u, thread %u (warp %u, role %s) waited %.1f ms for barrier %s[%u] "
+             "parity %u at tile iteration %lld",
+             kKernel[k < 4 ? k : 0], (unsigned)(r[2] >> 32), (unsigned)(r[2] & 0xffffffffu),
+             (unsigned)(r[2] & 0xffffffffu) / 32, kRole[role < 5 ? role : 0], (double)r[5] * 1e-6, kBar[bar < 6 ? bar : 0],
+             (unsigned)(r[3] >> 32), (unsigned)(r[3] & 0xffffffffu), (long long)r[4]);
+  return 1;
+}
+
+extern "C" size_t gnb_packed_linear_bytes(int M, int K) {
+  if (M <= 0 || K <= 0) return 0;
+  return (size_t)((M + tc::kM - 1) / tc::kM) * 2 * tc::kM * K * sizeof(__half);
+}
+
+extern "C" int gnb_pack_linear_tc(const float* W, int M, int K, void* Wp, void* stream) {
+  GNB_REQUIRE(W && Wp && M > 0 && K > 0 && K % 16 == 0, "gnb_pack_linear_tc: bad arguments (M=%d K=%d)", M, K);
+  const int nblk = (M + tc::kM - 1) / tc::kM;
+  const int64_t total = (int64_t)nblk * tc::kM * K;
+  unsigned blocks = (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  tc::pack_linear_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, M, K, (__half*)Wp, nblk);
+  return check_launch("gnb_pack_linear_tc");
+}
 
 extern "C" size_t gnb_split16_bytes(int64_t rows, int K) {
   if (rows < 0 || K <= 0) return 0;

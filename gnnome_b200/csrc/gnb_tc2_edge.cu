@@ -13,7 +13,11 @@
 //   warp 0      : producer: TMA loads (lane 0) + the tile's (src, dst) indices into the stage's index area
 //   warp 1      : MMA issue (one lane)
 //   warps 2, 3  : TMA stores, one thread per two epilogue groups, polling (store the finished stage of whichever
-//                 group is ready, release the stage)
+//                 group is ready, release the stage).  The hand-over barrier sfull is PER STAGE: a stage cannot be
+//                 armed again before it has been stored and reloaded, so its phases can never run ahead of the
+//                 store thread (a per-group barrier could complete two phases while the store thread was busy with
+//                 its other group -- the parity test then never succeeds: the round-1 cfg3 dead-lock).
+//   Every wait is bounded by the spin watchdog (gnb_tc.cuh): a lost phase traps with a record instead of spinning.
 //   warps 4..19 : epilogue, 4 groups x 4 TMEM lane quarters; group g takes tiles g, g+4, ... (one 32-edge chunk).
 //                 A thread owns ONE channel and walks its 32 consecutive edges: gathers of the (B1h, A2h) node
 //                 rows are coalesced across the warp, per-destination sums are register accumulators closed at
@@ -45,8 +49,7 @@ struct Edge2Cfg {
   // has been read from global memory on behalf of both)
   static constexpr bool MC = NH == 2;
   using T = Tile2<H, kE2NT>;
-  // Stages: one per group in its epilogue plus two being loaded / multiplied ahead.  NB <= 2 * groups: an epilogue
-  // group can never run two tiles ahead of its store warp (see sfull).
+  // Stages: one per group in its epilogue plus two being loaded / multiplied ahead.
   static constexpr int NB = (H >= 256) ? 6 : 8;
   // epilogue warps of a group that own live channels (the others idle: they must not feed the barriers, or they
   // would run ahead of the live ones and complete a phase early)
@@ -56,14 +59,6 @@ struct Edge2Cfg {
   static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 512;
 };
 
-__device__ __forceinline__ void red_release_add2(int32_t* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire2(const int32_t* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint16_t lds_u16(uint32_t addr) {
   uint16_t v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -77,8 +72,8 @@ template <int H, bool kResidual, bool kTiming>
 __global__ void __launch_bounds__(kE2Threads, 1)
 edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ Wp,
                         const float* __restrict__ scale_e, const float* __restrict__ shift_e,
-                        float* __restrict__ F, float* __restrict__ carry, int32_t* tile_flags, int epoch, int flags,
-                        int workers, unsigned long long* timing) {
+                        float* __restrict__ F, float* __restrict__ carry, int flags, int workers,
+                        unsigned long long* timing, const Watch watch, int store_delay_ns) {
   using C = Edge2Cfg<H>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -91,8 +86,9 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   uint64_t* empty = full + C::NB;           // [NB] store warp -> producer
   uint64_t* dfull = empty + C::NB;          // [D]  MMA -> epilogue
   uint64_t* dempty = dfull + kE2DBufs;      // [D]  epilogue -> MMA
-  uint64_t* sfull = dempty + kE2DBufs;      // [G]  epilogue (e' written into the stage) -> store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + kE2Groups);
+  uint64_t* sfull = dempty + kE2DBufs;      // [NB] epilogue (e' written into the stage) -> store warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + C::NB);
+  static_assert((3 * C::NB + 2 * kE2DBufs) * 8 + 4 <= 512, "barrier area");
 
   const int half = blockIdx.x % C::NH, worker = blockIdx.x / C::NH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,12 +99,12 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     for (int i = 0; i < C::NB; ++i) {
       mbar_init(&full[i], 33);
       mbar_init(&empty[i], C::MC ? 2 : 1);   // multicast: both CTAs of the cluster write into a stage
+      mbar_init(&sfull[i], C::LIVE_WARPS);
     }
     for (int i = 0; i < kE2DBufs; ++i) {
       mbar_init(&dfull[i], 1);
       mbar_init(&dempty[i], C::LIVE_WARPS);
     }
-    for (int i = 0; i < kE2Groups; ++i) mbar_init(&sfull[i], C::LIVE_WARPS);
     fence_barrier_init();
     prefetch_tensormap(&map_e);
   }
@@ -156,7 +152,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
       prefetch_rows(cur);
-      mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
+      mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkEdge2, kWrProducer, kWbEmpty), s, i);
       if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
@@ -185,11 +181,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB, d = i % kE2DBufs;
-      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
-      // both channel halves read whole rows of e and overwrite their own half in place: tell the other half
-      // that this CTA's copy of tile t has left global memory
-      if (C::NH > 1 && !C::MC && lane == 0) red_release_add2(tile_flags + t, 1);
-      mbar_wait_sleep(&dempty[d], ((i / kE2DBufs) & 1) ^ 1, 32);
+      mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbFull), s, i);
+      mbar_wait(&dempty[d], ((i / kE2DBufs) & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbDEmpty), d, i);
       tc_fence_after();
       if (elect_one()) {
         issue_tile_mma_sw128<H, kE2NT>(tmem_base, tmem_base + C::D_COL0 + d * kE2NT,
@@ -201,10 +194,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   } else if (warp < kE2FirstEpiWarp) {
     // ---------------------------------------------------------------- TMA store of one epilogue group
     // Lane 0 of warp 2 stores the tiles of groups 0 and 1, lane 0 of warp 3 those of groups 2 and 3.  It POLLS its
-    // two groups without blocking on either, so that each group's phases of sfull are consumed in order and
-    // promptly whatever the other group does (blocking on one group while the other runs two phases ahead would
-    // alias the phase parity and dead-lock; two lanes of one warp spinning on different barriers could starve
-    // each other).  Since the producer loads tiles in order and NB <= 8, a group is never two phases ahead.
+    // two groups without blocking on either (two lanes of one warp spinning on different barriers starved each
+    // other), testing the sfull barrier of the STAGE the group's next tile lives in.
     if (lane == 0) {
       constexpr int kFirst = (kE2Groups + 1) / 2;          // warp 2 serves groups [0, kFirst), warp 3 the rest
       const int g0 = (warp == 2) ? 0 : kFirst;
@@ -219,18 +210,16 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         for (int k = 0; k < kFirst; ++k) r = r || remaining(k);
         return r;
       };
+      SpinGuard guard;
       while (any_remaining()) {
         bool progressed = false;
 #pragma unroll
         for (int k = 0; k < kFirst; ++k) {
           if (!remaining(k)) continue;
-          const int i = it[k], grp = g0 + k;
-          if (!mbar_test(&sfull[grp], (i / kE2Groups) & 1)) continue;
-          const int64_t t = worker + (int64_t)i * workers;
+          const int i = it[k];
           const int s = i % C::NB;
-          if (C::NH > 1 && !C::MC) {  // the other half must have read tile t before our channels of it are overwritten
-            while (ld_acquire2(tile_flags + t) < C::NH * epoch) __nanosleep(32);
-          }
+          if (!mbar_test(&sfull[s], (i / C::NB) & 1)) continue;
+          const int64_t t = worker + (int64_t)i * workers;
           const uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
 #pragma unroll
           for (int kbl = 0; kbl < C::HC / kKB; ++kbl) {
@@ -240,12 +229,20 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           }
           tma_store_commit();
           tma_store_wait_read();
-          mbar_arrive(&empty[s]);
-          if (C::MC) mbar_arrive_cluster(&empty[s], (uint32_t)(half ^ 1));   // the peer also writes into this stage
+          if (store_delay_ns > 0) __nanosleep((unsigned)store_delay_ns);   // fault injection (gnb_debug_store_delay_ns)
+          if (store_delay_ns >= 0) {   // < 0: the stage is never released -- the watchdog test's dead-lock
+            mbar_arrive(&empty[s]);
+            if (C::MC) mbar_arrive_cluster(&empty[s], (uint32_t)(half ^ 1));   // the peer also writes into this stage
+          }
           it[k] += kE2Groups;
           progressed = true;
         }
-        if (!progressed) __nanosleep(32);
+        if (progressed) {
+          guard = SpinGuard();
+        } else {
+          __nanosleep(32);
+          guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbSFull), (uint32_t)(it[0] % C::NB), (uint32_t)((it[0] / C::NB) & 1), it[0]);
+        }
       }
       tma_store_wait_all();
     }
@@ -267,17 +264,14 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     //   (c / 64) * KB_BYTES + row * 128 + ((((c % 64) / 8) ^ (row % 8)) * 16) + (c % 8) * 2
     const uint32_t col_base = (uint32_t)((c >> 6) * T::KB_BYTES + sub * kE2Chunk * 128 + ((c & 7) << 1));
     const uint32_t col_x = (uint32_t)((c & 63) >> 3);
-    // Hand a finished stage to the store warp.  A warp must not arrive for its group's tile j before phase j-1 of
-    // sfull has completed (a warp with little to do -- the empty half of a ragged last tile -- could otherwise
-    // complete the previous phase on behalf of a slower warp that is still writing its rows).
+    // Hand a finished stage to the store warp: every live warp of the group arrives on the STAGE's sfull.  All
+    // arrivals of the stage's previous use precede its store, its reload and hence the `full` phase this warp has
+    // waited for, so a fast warp can never complete a phase on behalf of a slower one.
     // optional cycle accounting (gnb_debug_edge_timing): [full wait, dfull wait, batches, flush + hand-off, tiles]
     unsigned long long tm[5] = {0, 0, 0, 0, 0};
-    int jj = 0;   // tiles of this group handled so far
-    auto stage_done = [&]() {
-      if (jj > 0) mbar_wait(&sfull[grp], (jj - 1) & 1);
+    auto stage_done = [&](int s) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[grp]);
-      ++jj;
+      if (lane == 0) mbar_arrive(&sfull[s]);
     };
     int i = 0;
     for (int64_t t = worker; t < my_tiles; t += workers, ++i) {
@@ -288,15 +282,16 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       const bool live = cs < E;              // warp-uniform; false only for the second half of a ragged last tile
       const int n = live ? (int)((E - cs < kE2Chunk) ? (E - cs) : kE2Chunk) : 0;
       const long long t0 = kTiming ? clock64() : 0;
-      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);  // indices published (and the operand tile has landed)
+      // indices published (and the operand tile has landed)
+      mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbFull), s, i);
       const long long t1 = kTiming ? clock64() : 0;
       if (!live) {  // nothing to compute, but the barriers still have to be fed
-        mbar_wait_sleep(&dfull[d], dpar);
+        mbar_wait(&dfull[d], dpar, 64, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbDFull), d, i);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dempty[d]);
-        stage_done();
+        stage_done(s);
         continue;
       }
       const int* ia = idx_area + s * kE2IdxInts;
@@ -434,7 +429,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       float fb0[kEB], fb1[kEB];
       fetch(0, fa0, fb0);
       const long long t2 = kTiming ? clock64() : 0;
-      mbar_wait_sleep(&dfull[d], dpar, 32);
+      mbar_wait(&dfull[d], dpar, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbDFull), d, i);
       tc_fence_after();
       const long long t3 = kTiming ? clock64() : 0;
       auto run_chunk = [&](auto full_tag) {
@@ -461,7 +456,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       }
       // e' is in the stage: make it visible to the async proxy, then hand the stage to the store warp
       fence_proxy_async();
-      stage_done();
+      stage_done(s);
       if (kTiming) {
         const long long t5 = clock64();
         tm[0] += t1 - t0; tm[1] += t3 - t2; tm[2] += (t4 - t3) + (t2 - t1); tm[3] += t5 - t4; tm[4] += 1;
@@ -480,11 +475,13 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 
 // debugging aid: when set, every epilogue warp leaves its cycle accounting in timing[blockIdx][warp][5]
 static unsigned long long* g_edge_timing = nullptr;
+// fault injection: stall the store thread this long after every tile (the schedule must tolerate a slow store thread)
+static int g_store_delay_ns = 0;
 
 template <int H>
 static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t ldP, const void* Wp,
                                  const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
-                                 int32_t* tile_flags, int epoch, int flags, cudaStream_t stream) {
+                                 int flags, cudaStream_t stream) {
   using C = Edge2Cfg<H>;
   const bool res = flags & GNB_F_RESIDUAL;
   auto kern = g_edge_timing ? (res ? edge_forward_tc2_kernel<H, true, true> : edge_forward_tc2_kernel<H, false, true>)
@@ -494,7 +491,6 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
     set_error("gnb_edge_forward_tc2: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(err));
     return (int)err;
   }
-  if (C::NH > 1) GNB_REQUIRE(tile_flags != nullptr && epoch > 0, "gnb_edge_forward_tc2: H=%d needs tile_flags and epoch >= 1", H);
   const int64_t E = g->num_edges;
   CUtensorMap map_e;
   int rc = make_state_map(&map_e, e16, E, H, kE2NT);
@@ -502,7 +498,6 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
   const int64_t num_tiles = (E + kE2NT - 1) / kE2NT;
   int workers = sm_count() / C::NH;
   if (workers > num_tiles) workers = (int)num_tiles;
-  // every CTA must be resident at the same time (the channel halves wait on each other's flags)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(workers * C::NH));
   cfg.blockDim = dim3(kE2Threads);
@@ -515,8 +510,8 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  err = cudaLaunchKernelEx(&cfg, kern, map_e, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, tile_flags, epoch,
-                           flags, workers, g_edge_timing);
+  err = cudaLaunchKernelEx(&cfg, kern, map_e, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, flags, workers,
+                           g_edge_timing, watch_get(), g_store_delay_ns);
   if (err != cudaSuccess) {
     set_error("gnb_edge_forward_tc2: launch failed: %s", cudaGetErrorString(err));
     return (int)err;
@@ -531,11 +526,15 @@ using namespace gnb;
 
 extern "C" int gnb_edge_tile_tc2(int H) { return (H == 64 || H == 128 || H == 256) ? tc::kE2NT : GNB_E_INVALID; }
 
+extern "C" int gnb_edge_chunk_tc2(int H) { return (H == 64 || H == 128 || H == 256) ? tc::kE2Chunk : GNB_E_INVALID; }
+
 extern "C" void gnb_debug_edge_timing(void* buf) { tc::g_edge_timing = (unsigned long long*)buf; }
+
+extern "C" void gnb_debug_store_delay_ns(int ns) { tc::g_store_delay_ns = ns; }
 
 extern "C" int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
                                     const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
-                                    int32_t* tile_flags, int epoch, int flags, void* stream) {
+                                    int flags, void* stream) {
   GNB_REQUIRE(g != nullptr && g->num_edges >= 0 && g->in_ptr != nullptr, "graph not staged");
   if (g->num_edges == 0) return 0;
   GNB_REQUIRE(g->in_src && g->in_dst, "graph not staged");
@@ -546,9 +545,9 @@ extern "C" int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P,
               "gnb_edge_forward_tc2: e16 must be 16-byte aligned, P 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   switch (H) {
-    case 64: return tc::edge_forward_tc2_impl<64>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags, s);
-    case 128: return tc::edge_forward_tc2_impl<128>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags, s);
-    case 256: return tc::edge_forward_tc2_impl<256>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags, s);
+    case 64: return tc::edge_forward_tc2_impl<64>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, flags, s);
+    case 128: return tc::edge_forward_tc2_impl<128>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, flags, s);
+    case 256: return tc::edge_forward_tc2_impl<256>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, flags, s);
   }
   set_error("gnb_edge_forward_tc2: hidden_features=%d unsupported (64, 128, 256)", H);
   return GNB_E_INVALID;

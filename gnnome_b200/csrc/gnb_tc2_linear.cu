@@ -35,7 +35,7 @@ struct Lin2Cfg {
 template <int K, bool kMC>
 __global__ void __launch_bounds__(kLin2Threads, 1)
 node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, const __half* __restrict__ Wp, const float* __restrict__ bias, int M,
-                       float* __restrict__ out, int64_t ld_out, int nblk, int workers) {
+                       float* __restrict__ out, int64_t ld_out, int nblk, int workers, const Watch watch) {
   using C = Lin2Cfg<K>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -83,7 +83,7 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
-      mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
+      mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkLinear2, kWrProducer, kWbEmpty), s, i);
       if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
@@ -105,8 +105,8 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB, d = i & 1;
-      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
-      mbar_wait_sleep(&dempty[d], ((i >> 1) & 1) ^ 1, 32);
+      mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkLinear2, kWrMma, kWbFull), s, i);
+      mbar_wait(&dempty[d], ((i >> 1) & 1) ^ 1, 32, watch, watch_tag(kWkLinear2, kWrMma, kWbDEmpty), d, i);
       tc_fence_after();
       if (elect_one()) {
         issue_tile_mma_sw128<K, kLin2NT>(tmem_base, tmem_base + C::D_COL0 + d * kLin2NT,
@@ -126,7 +126,7 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       if ((i & 1) != g) continue;
-      mbar_wait_sleep(&dfull[g], (i >> 1) & 1, 32);
+      mbar_wait(&dfull[g], (i >> 1) & 1, 32, watch, watch_tag(kWkLinear2, kWrEpilogue, kWbDFull), g, i);
       tc_fence_after();
       uint32_t v0[32], v1[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + g * kLin2NT;
@@ -195,7 +195,7 @@ static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, map_x, rows, (const __half*)Wp, bias, M, out, ld_out, nblk, workers);
+  e = cudaLaunchKernelEx(&cfg, kern, map_x, rows, (const __half*)Wp, bias, M, out, ld_out, nblk, workers, watch_get());
   if (e != cudaSuccess) {
     set_error("gnb_node_linear_tc2: launch failed: %s", cudaGetErrorString(e));
     return (int)e;

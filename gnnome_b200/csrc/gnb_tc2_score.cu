@@ -32,7 +32,7 @@ template <int H, int HS>
 __global__ void __launch_bounds__(kS2Threads, 1)
 score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g, const float* __restrict__ S, const __half* __restrict__ Wp,
                          const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ W3,
-                         const float* __restrict__ b3, float* __restrict__ scores) {
+                         const float* __restrict__ b3, float* __restrict__ scores, const Watch watch) {
   using C = Score2Cfg<H, HS>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -114,7 +114,7 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
       prefetch_rows(cur);
-      mbar_wait_sleep(&empty[s], ((i / C::NB) & 1) ^ 1);
+      mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkScore2, kWrProducer, kWbEmpty), s, i);
       if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
         mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
@@ -141,8 +141,8 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB, d = i % kS2Groups;
-      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
-      mbar_wait_sleep(&dempty[d], ((i / kS2Groups) & 1) ^ 1, 32);
+      mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkScore2, kWrMma, kWbFull), s, i);
+      mbar_wait(&dempty[d], ((i / kS2Groups) & 1) ^ 1, 32, watch, watch_tag(kWkScore2, kWrMma, kWbDEmpty), d, i);
       tc_fence_after();
       if (elect_one()) {
         issue_tile_mma_sw128<H, kS2NT>(tmem_base, tmem_base + C::D_COL0 + d * kS2NT,
@@ -167,7 +167,7 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       if (i % kS2Groups != grp) continue;
       const int s = i % C::NB;
-      mbar_wait_sleep(&full[s], (i / C::NB) & 1, 32);
+      mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkScore2, kWrEpilogue, kWbFull), s, i);
       const int* ia = idx_area + s * kS2IdxInts;
       // copy what phase A / B need out of the stage's index area, then release our share of the stage
       const int my_src = ia[sub * 32 + lane];
@@ -175,7 +175,7 @@ score_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t 
       const int b_eid = ia[2 * kS2NT + w8 * 8 + my_edge];
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
-      mbar_wait_sleep(&dfull[grp], (i / kS2Groups) & 1, 32);
+      mbar_wait(&dfull[grp], (i / kS2Groups) & 1, 32, watch, watch_tag(kWkScore2, kWrEpilogue, kWbDFull), grp, i);
       tc_fence_after();
       // ---- phase A: hidden layer 1 for this warp's 32 edges x 32 units ---------------------------------
       if (unit_ok) {
@@ -280,7 +280,7 @@ static int score_forward_tc2_impl(const gnb_graph_t* g, const float* S, const vo
   int64_t grid = sm_count();
   if (grid > num_tiles) grid = num_tiles;
   score_forward_tc2_kernel<H, HS><<<(unsigned)grid, kS2Threads, C::SMEM, stream>>>(map_e, *g, S, (const __half*)Wp,
-                                                                                  W2, b2, W3, b3, scores);
+                                                                                  W2, b2, W3, b3, scores, watch_get());
   return check_launch("gnb_score_forward_tc2");
 }
 

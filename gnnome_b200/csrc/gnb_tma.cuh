@@ -38,6 +38,10 @@ struct Tile2 {
 // Returns 0 or a negative GNB_E_* code.
 int make_state_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows);
 
+// The watchdog argument of a tensor-core kernel launch: record in host-mapped memory (allocated on first use) and the
+// per-wait timeout (GNB_SPIN_TIMEOUT_MS or gnb_set_spin_timeout_ms; default 10 s, 0 = none).  gnb_tc2_common.cu.
+Watch watch_get();
+
 // ---------------------------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------------------------

@@ -67,6 +67,19 @@ class WalkGraph:
         if self.N % 2:
             raise ValueError('nodes come in strand pairs (2k, 2k + 1): num_nodes must be even')
         self._succ, self._pred = succ_csr, pred_csr
+        self.max_edge_id = -1
+        for csr in (succ_csr, pred_csr):
+            if csr is None:
+                continue
+            ptr, node, edge = csr
+            if ptr.shape != (self.N + 1,) or int(ptr[-1]) != node.size or edge.size != node.size:
+                raise ValueError('malformed CSR: ptr must have N + 1 entries and end at len(node) == len(edge)')
+            if node.size and (int(node.min()) < 0 or int(node.max()) >= self.N):
+                raise IndexError(f'neighbour id outside [0, {self.N}) in the successor / predecessor lists')
+            if edge.size:
+                if int(edge.min()) < 0:
+                    raise IndexError('negative edge id')
+                self.max_edge_id = max(self.max_edge_id, int(edge.max()))
         self._lib = _lib.load()
 
     @classmethod
@@ -112,6 +125,10 @@ class WalkGraph:
         n = cand.shape[0]
         src, dst = np.ascontiguousarray(cand[:, 0]), np.ascontiguousarray(cand[:, 1])
         logp = _np(log_probs, np.float32).reshape(-1)
+        if logp.size <= self.max_edge_id:   # the reference raises IndexError on logProbs[edges[...]] (inference.py:95)
+            raise IndexError(f'log_probs has {logp.size} entries but the graph refers to edge id {self.max_edge_id}')
+        if n and (int(cand.min()) < 0 or int(cand.max()) >= self.N):
+            raise IndexError(f'candidate endpoint outside [0, {self.N})')
         vis = self._visited_bytes(visited)
         off = np.zeros(n + 1, dtype=np.int64)
         back = np.zeros(max(n, 1), dtype=np.int64)
@@ -136,6 +153,10 @@ class WalkGraph:
         """inference.py:30-37: sum of ``prefix_length`` over the walk's edges + ``read_length`` of its last node."""
         w = _np(walk, np.int32)
         pl, rl = _np(prefix_length, np.int64), _np(read_length, np.int64)
+        if pl.size <= self.max_edge_id:
+            raise IndexError(f'prefix_length has {pl.size} entries but the graph refers to edge id {self.max_edge_id}')
+        if w.size and (int(w.min()) < 0 or int(w.max()) >= self.N or rl.size <= int(w.max())):
+            raise IndexError('walk node outside the graph / read_length')
         out = ctypes.c_int64(0)
         g = self._struct(self._succ)
         _lib.check(self._lib.gnb_walk_contig_length(ctypes.byref(g), pl.ctypes.data, rl.ctypes.data, w.ctypes.data, w.size,

@@ -55,7 +55,6 @@ class GraphIndex:
                        'gnb_graph_stage')
         self._keep = (src, dst)  # original-order endpoints (used by reversed())
         self._in_eid_long = None
-        self._tile_flags = {}
         del ws
 
     @property
@@ -69,30 +68,17 @@ class GraphIndex:
     def ref(self):
         return ctypes.byref(self.struct)
 
-    def chunk(self, H, backend='tc'):
-        """Carry granularity (edges per aggregation chunk) of the edge pass for this backend."""
+    def chunk(self, H, backend='tc2'):
+        """Carry granularity (edges per aggregation chunk) of the edge pass of this kernel family
+        ('tc2': gnb_edge_forward_tc2, 'ffma': gnb_edge_forward)."""
         lib = _lib.load()
-        chunk = lib.gnb_edge_chunk_tc(H) if backend == 'tc' else lib.gnb_edge_chunk(H)
+        chunk = lib.gnb_edge_chunk_tc2(H) if backend == 'tc2' else lib.gnb_edge_chunk(H)
         if chunk <= 0:
-            raise RuntimeError(f'hidden_features={H} unsupported (32, 64, 128, 256)')
+            raise RuntimeError(f'hidden_features={H} unsupported by the {backend!r} kernels')
         return chunk
 
-    def num_chunks(self, H, backend='tc'):
+    def num_chunks(self, H, backend='tc2'):
         return max(1, -(-self.E // self.chunk(H, backend)))
-
-    def tile_flags(self, H, backend='tc'):
-        """Zeroed int32[tiles] + launch counter for the H=256 channel-half handshake of gnb_edge_forward_tc / _tc2."""
-        lib = _lib.load()
-        tile = lib.gnb_edge_tile_tc2(H) if backend == 'tc2' else lib.gnb_edge_tile_tc(H)
-        st = self._tile_flags.get(tile)
-        if st is None:
-            st = self._tile_flags[tile] = [torch.zeros(max(1, -(-self.E // tile)), dtype=torch.int32,
-                                                       device=self.device), 0]
-        if st[1] >= 2 ** 29:  # keep NH * epoch inside int32
-            st[0].zero_()
-            st[1] = 0
-        st[1] += 1
-        return st[0], st[1]
 
     def reversed(self):
         """Index of ``dgl.reverse(g)`` (train.py:165): same edge ids, endpoints swapped."""

@@ -19,11 +19,10 @@ _SPLIT16_WIDTHS = (64, 128, 256)
 
 def set_backend(name):
     """'tc2' (default): TMA-fed tcgen05 kernels with the state held as split fp16 (hi, lo) images
-    (hidden_features 64 / 128 / 256; other widths fall back to 'tc');
-    'tc': first-generation tcgen05 kernels, fp32 state converted on the fly by producer warps;
-    'ffma': the CUDA-core fp32 kernels (bring-up path, kept as an on-device cross-check)."""
+    (hidden_features 64 / 128 / 256; hidden_features = 32 is too narrow for the 128-byte swizzle and runs 'ffma');
+    'ffma': the CUDA-core fp32 kernels -- an independent code path kept as the on-device cross-check."""
     global _BACKEND
-    if name not in ('tc2', 'tc', 'ffma'):
+    if name not in ('tc2', 'ffma'):
         raise ValueError(name)
     _BACKEND = name
 
@@ -35,7 +34,7 @@ def get_backend():
 def effective_backend(H):
     """The kernel family that actually runs a layer of width H under the current backend."""
     if _BACKEND == 'tc2':
-        return 'tc2' if H in _SPLIT16_WIDTHS else 'tc'
+        return 'tc2' if H in _SPLIT16_WIDTHS else 'ffma'
     return _BACKEND
 
 
@@ -108,7 +107,7 @@ class _GatedGCNBase(nn.Module):
         blocks_b.append(b(self.A_1))
         Wn = torch.cat(blocks_w, dim=0).contiguous()                 # [5H or 4H][H_in] (nn.Linear layout)
         bn = torch.cat(blocks_b, dim=0).contiguous()
-        if effective_backend(H) in ('tc', 'tc2'):
+        if effective_backend(H) == 'tc2':
             Wn_t, We_t = ops.pack_linear_tc(Wn), ops.pack_linear_tc(w(self.B_3).contiguous())
         else:
             Wn_t = Wn.t().contiguous()                               # k-major [H_in][5H or 4H]
@@ -135,7 +134,6 @@ class _GatedGCNBase(nn.Module):
         dev = h.device
         pk = self._pack(dev)
         ws = ws if ws is not None else {}
-        backend = 'ffma' if effective_backend(H) == 'ffma' else 'tc'
         n_blocks = 5 if self._symmetric else 4
         P = ws.get('P')
         if P is None or P.shape != (gi.N, n_blocks * H):
@@ -144,23 +142,17 @@ class _GatedGCNBase(nn.Module):
         if Fb is None or Fb.shape != (gi.N, H):
             Fb = ws['F'] = torch.empty((gi.N, H), dtype=torch.float32, device=dev)
         carry = ws.get('carry')
-        n_chunks = gi.num_chunks(H, backend)
+        n_chunks = gi.num_chunks(H, 'ffma')
         if carry is None or carry.shape != (n_chunks, 4, H):
             carry = ws['carry'] = torch.empty((n_chunks, 4, H), dtype=torch.float32, device=dev)
         h_out = ws.pop('h_spare', None)
         if h_out is None or h_out.shape != h.shape or h_out.data_ptr() == h.data_ptr():
             h_out = torch.empty_like(h)
         flags = self._flags()
-        if backend == 'tc':
-            ops.node_linear_tc(h, pk['Wn_t'], pk['bn'], n_blocks * H, out=P)
-            tile_flags, epoch = gi.tile_flags(H) if H > 128 else (None, 0)
-            ops.edge_forward_tc(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry,
-                                tile_flags, epoch, flags)
-        else:
-            ops.node_linear(h, pk['Wn_t'], pk['bn'], out=P)
-            ops.edge_forward(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry, flags)
+        ops.node_linear(h, pk['Wn_t'], pk['bn'], out=P)
+        ops.edge_forward(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, Fb, carry, flags)
         ops.node_update(gi, H, P, e_pos, Fb, carry, h, pk['scale_h'], pk['shift_h'], h_out, flags,
-                        gi.chunk(H, backend))
+                        gi.chunk(H, 'ffma'))
         ws['h_spare'] = h  # ping-pong: the caller no longer needs the input h
         return h_out, e_pos
 
@@ -185,7 +177,7 @@ class _GatedGCNBase(nn.Module):
 
         P = buf('P', (gi.N, n_blocks * H))
         Fb = buf('F', (gi.N, H))
-        carry = buf('carry', (gi.num_chunks(H, 'tc'), 4, H))
+        carry = buf('carry', (gi.num_chunks(H, 'tc2'), 4, H))
         h_out = ws.pop('h_spare', None)
         if h_out is None or h_out.shape != h32.shape or h_out.data_ptr() == h32.data_ptr():
             h_out = torch.empty_like(h32)
@@ -194,10 +186,9 @@ class _GatedGCNBase(nn.Module):
             h16_out = torch.empty_like(h16)
         flags = self._flags()
         ops.node_linear_tc2(h16, pk['Wn_t'], pk['bn'], n_blocks * H, out=P)
-        tile_flags, epoch = gi.tile_flags(H, 'tc2') if H > 128 else (None, 0)
-        ops.edge_forward_tc2(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e16, Fb, carry, tile_flags, epoch, flags)
+        ops.edge_forward_tc2(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e16, Fb, carry, flags)
         ops.node_update2(gi, H, P, e16, Fb, carry, h32, pk['scale_h'], pk['shift_h'], h_out, h16_out, flags,
-                         gi.chunk(H, 'tc'))
+                         gi.chunk(H, 'tc2'))
         ws['h_spare'], ws['h16_spare'] = h32, h16   # ping-pong: the caller no longer needs the inputs
         return h_out, h16_out, e16
 

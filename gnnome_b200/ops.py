@@ -113,19 +113,6 @@ def pack_linear_tc(W):
     return out
 
 
-def node_linear_tc(a, Wp, bias, M, out=None):
-    """out = a @ W.T + bias on the tensor cores; Wp = pack_linear_tc(W[M][K])."""
-    lib = _lib.load()
-    rows, K = a.shape
-    if out is None:
-        out = torch.empty((rows, M), dtype=torch.float32, device=a.device)
-    with _logged('gnb_node_linear_tc', a.device):
-        _lib.check(lib.gnb_node_linear_tc(_f32(a, 'a'), rows, K, Wp.data_ptr(), _f32(bias, 'bias'), M,
-                                          _f32(out, 'out'), out.stride(0), current_stream_ptr(a.device)),
-                   'gnb_node_linear_tc')
-    return out
-
-
 def edge_forward(gi: GraphIndex, H, P, We_t, scale_e, shift_e, e, F, carry, flags):
     lib = _lib.load()
     with _logged('gnb_edge_forward', e.device):
@@ -133,15 +120,6 @@ def edge_forward(gi: GraphIndex, H, P, We_t, scale_e, shift_e, e, F, carry, flag
                                         _f32(scale_e, 'scale_e'), _f32(shift_e, 'shift_e'), _f32(e, 'e'),
                                         _f32(F, 'F'), _f32(carry, 'carry'), flags,
                                         current_stream_ptr(e.device)), 'gnb_edge_forward')
-
-
-def edge_forward_tc(gi: GraphIndex, H, P, Wp, scale_e, shift_e, e, F, carry, tile_flags, epoch, flags):
-    lib = _lib.load()
-    with _logged('gnb_edge_forward_tc', e.device):
-        _lib.check(lib.gnb_edge_forward_tc(gi.ref(), H, _f32(P, 'P'), P.stride(0), Wp.data_ptr(),
-                                           _f32(scale_e, 'scale_e'), _f32(shift_e, 'shift_e'), _f32(e, 'e'),
-                                           _f32(F, 'F'), _f32(carry, 'carry'), _opt(tile_flags), epoch, flags,
-                                           current_stream_ptr(e.device)), 'gnb_edge_forward_tc')
 
 
 def node_update(gi: GraphIndex, H, P, e, F, carry, h_in, scale_h, shift_h, h_out, flags, chunk,
@@ -265,12 +243,12 @@ def node_linear_tc2(x16, Wp, bias, M, out=None):
     return out
 
 
-def edge_forward_tc2(gi: GraphIndex, H, P, Wp, scale_e, shift_e, e16, F, carry, tile_flags, epoch, flags):
+def edge_forward_tc2(gi: GraphIndex, H, P, Wp, scale_e, shift_e, e16, F, carry, flags):
     lib = _lib.load()
     with _logged('gnb_edge_forward_tc2', e16.device):
         _lib.check(lib.gnb_edge_forward_tc2(gi.ref(), H, _f32(P, 'P'), P.stride(0), Wp.data_ptr(),
                                             _f32(scale_e, 'scale_e'), _f32(shift_e, 'shift_e'), _img(e16, 'e16'),
-                                            _f32(F, 'F'), _f32(carry, 'carry'), _opt(tile_flags), epoch, flags,
+                                            _f32(F, 'F'), _f32(carry, 'carry'), flags,
                                             current_stream_ptr(e16.device)), 'gnb_edge_forward_tc2')
 
 

@@ -169,19 +169,20 @@ class CudaKernels:
     def node_linear_layer(self, pk, h, M, out):
         if isinstance(h, tuple):
             return self.ops.node_linear_tc2(h[1], pk['Wn_t'], pk['bn'], M, out=out)
-        return self.ops.node_linear_tc(h, pk['Wn_t'], pk['bn'], M, out=out)
+        return self.ops.node_linear(h, pk['Wn_t'], pk['bn'], out=out)
 
     def gather_rows(self, table, idx, out=None):
         return self.ops.gather_rows(table, idx, out=out)
 
     def edge_forward(self, gi, H, P, pk, e_pos, F, carry, flags):
-        tc2 = e_pos.dtype == torch.float16
-        tile_flags, epoch = gi.tile_flags(H, 'tc2' if tc2 else 'tc') if H > 128 else (None, 0)
-        fn = self.ops.edge_forward_tc2 if tc2 else self.ops.edge_forward_tc
-        fn(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, F, carry, tile_flags, epoch, flags)
+        fn = self.ops.edge_forward_tc2 if e_pos.dtype == torch.float16 else self.ops.edge_forward
+        fn(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, F, carry, flags)
+
+    def _family(self, H):
+        return 'tc2' if self._split(H) else 'ffma'
 
     def carry_shape(self, gi, H):
-        return (gi.num_chunks(H, 'tc'), 4, H)
+        return (gi.num_chunks(H, self._family(H)), 4, H)
 
     def reverse_partial(self, gi, H, P, e_pos, node_begin, node_end, out):
         fn = self.ops.reverse_partial2 if e_pos.dtype == torch.float16 else self.ops.reverse_partial
@@ -200,12 +201,12 @@ class CudaKernels:
             h32, h16 = h_in
             o32, o16 = self._like('h32', h32), self._like('h16', h16)
             self.ops.node_update2(gi, H, P, e_pos, F, carry, h32, pk['scale_h'], pk['shift_h'], o32, o16, flags,
-                                  gi.chunk(H, 'tc'), **kw)
+                                  gi.chunk(H, 'tc2'), **kw)
             self.spare['h32'], self.spare['h16'] = h32, h16
             return (o32, o16)
         out = self._like('h32', h_in)
         self.ops.node_update(gi, H, P, e_pos, F, carry, h_in, pk['scale_h'], pk['shift_h'], out, flags,
-                             gi.chunk(H, 'tc'), **kw)
+                             gi.chunk(H, 'ffma'), **kw)
         self.spare['h32'] = h_in
         return out
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 8
+#define GNB_ABI_VERSION 9
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -86,24 +86,14 @@ size_t gnb_packed_linear_bytes(int M, int K);
 /* W[M][K] (nn.Linear layout, fp32) -> packed fp16 (hi, lo) blocks at Wp (16-byte aligned). K % 16 == 0. */
 int gnb_pack_linear_tc(const float* W, int M, int K, void* Wp, void* stream);
 
-/* Same contract as gnb_node_linear with the weight given as gnb_pack_linear_tc(W[M][K]) output.
- * K in {32, 64, 128, 256}; X 32-byte aligned. */
-int gnb_node_linear_tc(const float* X, int64_t rows, int K, const void* Wp, const float* bias, int M,
-                       float* out, int64_t ld_out, void* stream);
-
-/* Carry granularity (edges per aggregation chunk) and tile size of gnb_edge_forward_tc. */
-int gnb_edge_chunk_tc(int H);
-int gnb_edge_tile_tc(int H);
-
-/* Tensor-core edition of gnb_edge_forward: same contract, with the edge weight given as
- * gnb_pack_linear_tc(B_3.weight [H][H]) and carry sized ceil(E / gnb_edge_chunk_tc(H)) x 4 x H.
- * For H = 256 the two 128-channel halves of a tile run on different CTAs and both read whole rows of e
- * before either overwrites its half: tile_flags is a caller-owned int32[ceil(E / gnb_edge_tile_tc(H))],
- * zeroed once, and epoch = 1, 2, 3, ... counts the launches that used it since (unused for H < 256).
- * e must be 32-byte aligned. */
-int gnb_edge_forward_tc(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
-                        const float* scale_e, const float* shift_e, float* e, float* F, float* carry,
-                        int32_t* tile_flags, int epoch, int flags, void* stream);
+/* Spin watchdog of the tensor-core kernels.  Every device-side barrier wait is bounded (default 10 s of wall
+ * clock per wait; GNB_SPIN_TIMEOUT_MS in the environment or gnb_set_spin_timeout_ms override it, 0 = unbounded):
+ * a wait that expires writes {kernel, block, thread, warp role, barrier, index, parity, tile iteration} into
+ * host-mapped memory and traps, so a lost barrier phase becomes a CUDA launch failure at the next
+ * synchronisation instead of a silent spin.  gnb_hang_report formats that record into buf (returns 1) or
+ * returns 0 when no wait has expired in this process; it needs no working CUDA context. */
+void gnb_set_spin_timeout_ms(long long ms);
+int gnb_hang_report(char* buf, size_t cap);
 
 /* Number of consecutive edge positions one aggregation chunk covers (carry granularity). */
 int gnb_edge_chunk(int H);
@@ -127,7 +117,7 @@ int gnb_edge_forward(const gnb_graph_t* g, int H, const float* P, int64_t ldP,
 /* Reverse aggregation over the src-CSR fused with the node update (gated_gcn_full.py:124-137):
  *   Bk_i = sum_{q: src_q = i} sigmoid(e'_q) * P[dst_q][A3h] / (sum_q sigmoid(e'_q) + 1e-6)   (symmetric only)
  *   h'_i = relu((P[i][A1h] + F_i + Bk_i) * scale_h + shift_h) (+ h_i if GNB_F_RESIDUAL)
- * chunk = carry granularity of the edge pass that produced F / carry (gnb_edge_chunk or gnb_edge_chunk_tc).
+ * chunk = carry granularity of the edge pass that produced F / carry (gnb_edge_chunk or gnb_edge_chunk_tc2).
  * Only nodes node_begin <= i < node_end are updated (single GPU: 0, num_nodes; h_in / h_out need rows
  * for those nodes only).  Multi-GPU (graph partitioned by destination range, the staged graph holds the
  * owned nodes followed by halo source nodes): xp_ptr[i] .. xp_ptr[i+1] index xp_row, whose entries are
@@ -192,23 +182,32 @@ int gnb_encode2(const float* in, const int32_t* idx, int64_t rows, int in_f, int
                 const float* W1, const float* b1, const float* W2t, const float* b2, void* out16,
                 float* out32, void* stream);
 
-/* gnb_node_linear_tc with X given as split16 images (gated_gcn_full.py:91-96, score_predictor.py:13-14). */
+/* gnb_node_linear on the tensor cores: X given as split16 images, the weight as gnb_pack_linear_tc(W[M][K]) output
+ * (gated_gcn_full.py:91-96, score_predictor.py:13-14).  K in {64, 128, 256}. */
 int gnb_node_linear_tc2(const void* X16, int64_t rows, int K, const void* Wp, const float* bias, int M,
                         float* out, int64_t ld_out, void* stream);
 
-/* Edges per tile of gnb_edge_forward_tc2 (tile_flags has ceil(E / this) entries). */
+/* Edges per tile and carry granularity (edges per aggregation chunk) of gnb_edge_forward_tc2. */
 int gnb_edge_tile_tc2(int H);
+int gnb_edge_chunk_tc2(int H);
 
-/* gnb_edge_forward_tc with the edge state e16 in split16 format, updated in place (gated_gcn_full.py:97,104-114).
- * Same P / carry / tile_flags / epoch contract (tile_flags sized with gnb_edge_tile_tc2); carry granularity
- * gnb_edge_chunk_tc(H). */
+/* Tensor-core edition of gnb_edge_forward (gated_gcn_full.py:97,104-114): same contract, with the edge state e16 in
+ * split16 format (updated in place), the edge weight given as gnb_pack_linear_tc(B_3.weight [H][H]) and carry sized
+ * ceil(E / gnb_edge_chunk_tc2(H)) x 4 x H.  H in {64, 128, 256}; for H = 256 the two 128-channel halves of a tile
+ * run on the two CTAs of a cluster that share the tile through TMA multicast. */
 int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
                          const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
-                         int32_t* tile_flags, int epoch, int flags, void* stream);
+                         int flags, void* stream);
 
 /* Debugging aid: buf = device uint64[SMs][32 warps][5] (or NULL to switch off); every epilogue warp of
  * gnb_edge_forward_tc2 then leaves its cycle accounting there (full wait, accumulator wait, compute, hand-off, tiles). */
 void gnb_debug_edge_timing(void* buf);
+
+/* Fault injection for the liveness tests: the TMA-store thread of gnb_edge_forward_tc2 sleeps ns nanoseconds after
+ * every tile it stores (0 = off).  The pipeline must terminate with unchanged results however slow that thread is.
+ * ns < 0: the thread never releases a stage -- a deliberate dead-lock that the spin watchdog must turn into a
+ * launch failure with a record (run it in a throw-away process: the CUDA context does not survive the trap). */
+void gnb_debug_store_delay_ns(int ns);
 
 /* gnb_node_update with e' read from split16 images; writes h' as fp32 rows (h_out, row i) and, if h16_out is
  * not NULL, as split16 images of the rows node_begin .. node_end (row i - node_begin) for the next layer's

@@ -70,8 +70,16 @@ def test_walker_edge_cases(fx):
     assert walk_f == [0, 2]
     with pytest.raises(ValueError, match='strand pairs'):
         WalkGraph.from_edge_list([0], [1], 3)
-    with pytest.raises(RuntimeError, match='out of range'):
+    with pytest.raises((RuntimeError, IndexError), match='out of range|outside'):
         wg.run_greedy_both_ways([(0, 9)], logp)
+    # a score vector shorter than the edge ids the lists refer to (stale {idx}_predicts.pt): the reference raises
+    # IndexError on logProbs[edges[...]]; reading past the end must never happen silently
+    with pytest.raises(IndexError, match='log_probs has 1 entries'):
+        wg.run_greedy_both_ways([(0, 2)], logp[:1])
+    with pytest.raises(IndexError, match='prefix_length has 2 entries'):
+        wg.get_contig_length([0, 2, 4], torch.ones(2, dtype=torch.int64), torch.ones(8, dtype=torch.int64))
+    with pytest.raises(IndexError, match='neighbour id outside'):
+        WalkGraph(4, (np.array([0, 1, 1, 1, 1]), np.array([7], dtype=np.int32), np.array([0], dtype=np.int32)))
     with pytest.raises(RuntimeError, match='no edge'):
         wg.get_contig_length([0, 4], torch.ones(3, dtype=torch.int64), torch.ones(8, dtype=torch.int64))
     assert wg.get_contig_length([0, 2, 4], torch.tensor([5, 7, 11]), torch.arange(8) * 100) == 5 + 7 + 400

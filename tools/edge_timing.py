@@ -26,9 +26,8 @@ with torch.no_grad():
     lib.gnb_debug_edge_timing(ctypes.c_void_p(buf.data_ptr()))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pk = conv._pack(e16.device)
-    tf, ep = gi.tile_flags(H, 'tc2') if H > 128 else (None, 0)
     ev0.record()
-    ops.edge_forward_tc2(gi, H, ws['P'], pk['We_t'], pk['scale_e'], pk['shift_e'], e16, ws['F'], ws['carry'], tf, ep, conv._flags())
+    ops.edge_forward_tc2(gi, H, ws['P'], pk['We_t'], pk['scale_e'], pk['shift_e'], e16, ws['F'], ws['carry'], conv._flags())
     ev1.record()
     torch.cuda.synchronize()
     lib.gnb_debug_edge_timing(None)
