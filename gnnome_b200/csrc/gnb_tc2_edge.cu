@@ -12,11 +12,10 @@
 //   e' written over it in place (same thread, same address)  ->  TMA store back to HBM.
 //   warp 0      : producer: TMA loads (lane 0) + the tile's (src, dst) indices into the stage's index area
 //   warp 1      : MMA issue (one lane)
-//   warps 2, 3  : TMA stores, one thread per two epilogue groups, polling (store the finished stage of whichever
-//                 group is ready, release the stage).  The hand-over barrier sfull is PER STAGE: a stage cannot be
-//                 armed again before it has been stored and reloaded, so its phases can never run ahead of the
-//                 store thread (a per-group barrier could complete two phases while the store thread was busy with
-//                 its other group -- the parity test then never succeeds: the round-1 cfg3 dead-lock).
+//   warps 2, 3  : TMA stores, one thread for the even stages, one for the odd ones, polling (store whichever finished stage
+//                 group is ready, release the stage).  The hand-over barrier sfull is PER STAGE and each stage has ONE
+//                 store thread: the barrier's phases are consumed in sequence by a single waiter, and a stage
+//                 cannot be armed again before that waiter has stored it and released it for reloading.
 //   Every wait is bounded by the spin watchdog (gnb_tc.cuh): a lost phase traps with a record instead of spinning.
 //   warps 4..19 : epilogue, 4 groups x 4 TMEM lane quarters; group g takes tiles g, g+4, ... (one 32-edge chunk).
 //                 A thread owns ONE channel and walks its 32 consecutive edges: gathers of the (B1h, A2h) node
@@ -193,31 +192,36 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     }
   } else if (warp < kE2FirstEpiWarp) {
     // ---------------------------------------------------------------- TMA store of one epilogue group
-    // Lane 0 of warp 2 stores the tiles of groups 0 and 1, lane 0 of warp 3 those of groups 2 and 3.  It POLLS its
-    // two groups without blocking on either (two lanes of one warp spinning on different barriers starved each
-    // other), testing the sfull barrier of the STAGE the group's next tile lives in.
+    // Lane 0 of warp 2 stores the tiles that pass through the even stages, lane 0 of warp 3 those of the odd stages.
+    // A stage's hand-over barrier thus has ONE consumer that sees every phase of it in sequence: it tests phase k
+    // only after it has stored phase k - 1, and phase k + 1 cannot complete before it releases the stage -- the
+    // parity test can neither alias forwards nor be satisfied by the phase before last.  (Round 1 assigned the
+    // stores by epilogue GROUP with one barrier per group: a group could complete two phases while the thread was
+    // busy with its other group -- the cfg3 dead-lock.  One barrier per stage polled by the group's thread is wrong
+    // the other way round: with NB = 6 a stage alternates between two groups, so each thread saw every OTHER phase
+    // and a fresh barrier satisfied its parity test before the tile had even been processed.)
+    // The thread POLLS its stages without blocking on any of them (tiles of different groups finish out of order).
     if (lane == 0) {
-      constexpr int kFirst = (kE2Groups + 1) / 2;          // warp 2 serves groups [0, kFirst), warp 3 the rest
-      const int g0 = (warp == 2) ? 0 : kFirst;
-      const int ng = (warp == 2) ? kFirst : kE2Groups - kFirst;
-      int it[kFirst];                                      // next tile iteration index of each served group
+      const int l0 = warp - 2;                              // stages l0, l0 + 2, ...
+      constexpr int kMaxSt = (C::NB + 1) / 2;
+      int it[kMaxSt];                                       // next tile iteration that passes through each served stage
 #pragma unroll
-      for (int k = 0; k < kFirst; ++k) it[k] = g0 + k;
-      auto remaining = [&](int k) { return k < ng && worker + (int64_t)it[k] * workers < num_tiles; };
+      for (int k = 0; k < kMaxSt; ++k) it[k] = l0 + 2 * k;
+      auto remaining = [&](int k) { return l0 + 2 * k < C::NB && worker + (int64_t)it[k] * workers < num_tiles; };
       auto any_remaining = [&]() {
         bool r = false;
 #pragma unroll
-        for (int k = 0; k < kFirst; ++k) r = r || remaining(k);
+        for (int k = 0; k < kMaxSt; ++k) r = r || remaining(k);
         return r;
       };
       SpinGuard guard;
       while (any_remaining()) {
         bool progressed = false;
 #pragma unroll
-        for (int k = 0; k < kFirst; ++k) {
+        for (int k = 0; k < kMaxSt; ++k) {
           if (!remaining(k)) continue;
           const int i = it[k];
-          const int s = i % C::NB;
+          const int s = l0 + 2 * k;                         // == i % NB
           if (!mbar_test(&sfull[s], (i / C::NB) & 1)) continue;
           const int64_t t = worker + (int64_t)i * workers;
           const uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
@@ -234,14 +238,14 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
             mbar_arrive(&empty[s]);
             if (C::MC) mbar_arrive_cluster(&empty[s], (uint32_t)(half ^ 1));   // the peer also writes into this stage
           }
-          it[k] += kE2Groups;
+          it[k] += C::NB;
           progressed = true;
         }
         if (progressed) {
           guard = SpinGuard();
         } else {
           __nanosleep(32);
-          guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbSFull), (uint32_t)(it[0] % C::NB), (uint32_t)((it[0] / C::NB) & 1), it[0]);
+          guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbSFull), (uint32_t)l0, (uint32_t)((it[0] / C::NB) & 1), it[0]);
         }
       }
       tma_store_wait_all();
