@@ -57,7 +57,7 @@ SIGNATURES = {
     'gnb_node_linear_tc2': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
     'gnb_edge_tile_tc2': (_I, [_I]),
     'gnb_edge_chunk_tc2': (_I, [_I]),
-    'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _I, _P]),
+    'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _I, _P]),
     'gnb_debug_edge_timing': (None, [_P]),
     'gnb_debug_store_delay_ns': (None, [_I]),
     'gnb_node_update2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),
@@ -90,7 +90,7 @@ SIGNATURES = {
     'gnb_walk_jumped_nodes': (_I, [ctypes.POINTER(GnbWalkGraph), ctypes.POINTER(GnbWalkGraph), _P, _L, _P]),
 }
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 

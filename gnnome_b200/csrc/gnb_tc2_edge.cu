@@ -3,6 +3,12 @@
 //   z_p  = B1h[src_p] + B2h[dst_p] + e_p * W_B3^T         (E x H x H product on tcgen05, fp16 hi/lo split, fp32 in TMEM)
 //   e'_p = relu(z_p * scale + shift) (+ e_p)               written over e in place
 //   F_i  = sum_{p: dst_p = i} sigmoid(e'_p) * A2h[src_p] / (sum_p sigmoid(e'_p) + 1e-6)
+// The eval-mode norm affine is folded into the operands by the caller: the rows of W_B3 and B_1 are multiplied by
+// scale, B2h' = scale * B2h + shift, so that the epilogue computes  relu(D + B1h'[src] + B2h'[dst]) / 16 + e/16  in
+// the scaled domain the split16 state is stored in.  The residual e/16 = hi + lo is read from TENSOR MEMORY too: a
+// second, identity product (A = I from shared memory, B = the stage's own k blocks of this CTA's channels) puts it
+// there in the accumulator layout, exactly (one product per output), instead of two 16-bit shared loads, two
+// conversions and two floating-point operations per element in the issue-bound epilogue.
 //
 // Persistent CTAs, one per SM; a CTA owns HC = min(H, 128) output channels (H = 256: the two channel halves of a
 // tile run on neighbouring CTAs) with its W_B3 block resident in TMEM, and walks 32-edge tiles of the dst-sorted
@@ -22,6 +28,12 @@
 //                 rows are coalesced across the warp, per-destination sums are register accumulators closed at
 //                 warp-uniform segment boundaries (no atomics, fixed summation order).  Segments that straddle
 //                 a 32-edge chunk leave partial sums in carry[chunk][4][H], resolved by gnb_node_update2.
+//                 e' goes back through TENSOR MEMORY: the thread writes its fp32 values over the residual columns of
+//                 the accumulator set (its own lane), and after the tile the warp reads its 32 lanes back in the
+//                 matrix-fragment layout (tcgen05.ld.16x256b: a thread then holds pairs of consecutive edges of one
+//                 channel), splits the pairs into fp16 (hi, lo) with packed conversions and stores 8 x 8 blocks
+//                 TRANSPOSED into the stage with stmatrix -- 16-byte rows of 8 channels in the 128-byte swizzle --
+//                 instead of two 16-bit shared stores and the lane extraction per element.
 #include <type_traits>
 
 #include "gnb_tma.cuh"
@@ -33,7 +45,7 @@ constexpr int kE2NT = 32;        // edges per tile (MMA N) = edges per epilogue 
 constexpr int kE2Chunk = kE2NT;
 constexpr int kE2Groups = 4;     // epilogue groups of four warps (one per TMEM lane quarter); group g takes tiles g, g+G, ...
                                  // (five groups were measured slower: the schedulers are issue-bound, r01h)
-constexpr int kE2DBufs = 8;      // accumulator buffers (two per group: the MMA of a group's next tile overlaps its epilogue)
+constexpr int kE2DCols = 2 * kE2NT;   // TMEM columns of one accumulator set: z (32 edges) | residual e/16 (32 edges)
 constexpr int kE2FirstEpiWarp = 4;
 constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 4 * kE2Groups);
 constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[32], dst[32], prev_dst, next_dst (+ pad: stages stay 16-byte aligned)
@@ -49,28 +61,88 @@ struct Edge2Cfg {
   static constexpr bool MC = NH == 2;
   using T = Tile2<H, kE2NT>;
   // Stages: one per group in its epilogue plus two being loaded / multiplied ahead.
-  static constexpr int NB = (H >= 256) ? 6 : 8;
+  static constexpr int NB = (H >= 256) ? 5 : 8;
+  // accumulator sets in TMEM: one per epilogue group (H = 256: the weight images take half of the 512 columns).  The
+  // MMA of a group's next tile waits for its epilogue; the other three groups hide that.  Set d is used by group d
+  // only, so each of its barriers has one producer and one consumer that sees every phase in sequence.
+  static constexpr int DB = kE2Groups;
+  // the identity block [128 rows (TMEM lanes)][HC input channels] as a K-major SWIZZLE_128B A operand
+  static constexpr int ID_KB_BYTES = kM * 128;
+  static constexpr int ID_BYTES = (HC / kKB) * ID_KB_BYTES;
   // epilogue warps of a group that own live channels (the others idle: they must not feed the barriers, or they
   // would run ahead of the live ones and complete a phase early)
   static constexpr int LIVE_WARPS = HC / 32;
-  static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + kE2DBufs * kE2NT);
+  static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + DB * kE2DCols);
   static constexpr uint32_t D_COL0 = 2 * T::W_COLS;
-  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 512;
+  static_assert(2 * T::W_COLS + DB * kE2DCols <= 512, "tensor memory budget");
+  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + ID_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 512;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
-__device__ __forceinline__ uint16_t lds_u16(uint32_t addr) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-  return v;
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]; one thread issues for the CTA
+__device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+
+// The residual product: D[c][edge] = sum_k I[c][k] * (Xhi + Xlo)[edge][k] over the KI input channels this CTA owns
+// (b_addr = the stage's first k block of those channels; the lo image follows img_bytes later).
+template <int KI, int NT>
+__device__ __forceinline__ void issue_ident_mma_sw128(uint32_t tmem_d, uint32_t ident_addr, uint32_t b_addr,
+                                                      uint32_t img_bytes, uint32_t kb_bytes) {
+  constexpr uint32_t idesc = make_idesc(kM, NT);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int img = 0; img < 2; ++img) {
+#pragma unroll
+    for (int ks = 0; ks < KI / 16; ++ks) {
+      const uint32_t a = ident_addr + (ks >> 2) * (kM * 128) + (ks & 3) * 32;
+      const uint32_t b = b_addr + img * img_bytes + (ks >> 2) * kb_bytes + (ks & 3) * 32;
+      mma_ss_f16(tmem_d, make_sw128_desc(a), make_sw128_desc(b), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+// sigmoid(16 x): the state is held in the scaled domain x = e / 16
+__device__ __forceinline__ float sigmoid16f_fast(float x) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-16.0f * 1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return r;
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+// 16 TMEM lanes x 32 columns in the matrix-fragment layout (measured, tools/microbench/tmem_probe.cu): register
+// r[4c + 2a + b] of thread T holds (lane0 + T / 4 + 8a, column 8c + 2 (T % 4) + b)
+__device__ __forceinline__ void tmem_ld_frag16x32(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// four 8 x 8 b16 matrices, transposed on the way: memory[m][i][j] = half (i % 2) of register m of thread 4j + i / 2;
+// thread T supplies the address of row T % 8 of matrix T / 8 (16 bytes)
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3)
+               : "memory");
 }
 
 template <int H, bool kResidual, bool kTiming>
 __global__ void __launch_bounds__(kE2Threads, 1)
 edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ Wp,
-                        const float* __restrict__ scale_e, const float* __restrict__ shift_e,
                         float* __restrict__ F, float* __restrict__ carry, int flags, int workers,
                         unsigned long long* timing, const Watch watch, int store_delay_ns) {
   using C = Edge2Cfg<H>;
@@ -79,15 +151,16 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   // 1024-byte alignment by pointer arithmetic on the shared array (an integer round-trip would demote every later
   // access through these pointers to generic loads)
   uint8_t* bufs = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  int* idx_area = reinterpret_cast<int*>(bufs + (size_t)C::NB * T::BUF_BYTES);
+  uint8_t* ident = bufs + (size_t)C::NB * T::BUF_BYTES;
+  int* idx_area = reinterpret_cast<int*>(ident + C::ID_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(idx_area + C::NB * kE2IdxInts);
   uint64_t* full = bars;                    // [NB] producer (TMA bytes + 32 index lanes) -> MMA, epilogue
   uint64_t* empty = full + C::NB;           // [NB] store warp -> producer
   uint64_t* dfull = empty + C::NB;          // [D]  MMA -> epilogue
-  uint64_t* dempty = dfull + kE2DBufs;      // [D]  epilogue -> MMA
-  uint64_t* sfull = dempty + kE2DBufs;      // [NB] epilogue (e' written into the stage) -> store warp
+  uint64_t* dempty = dfull + C::DB;         // [D]  epilogue -> MMA
+  uint64_t* sfull = dempty + C::DB;         // [NB] epilogue (e' written into the stage) -> store warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + C::NB);
-  static_assert((3 * C::NB + 2 * kE2DBufs) * 8 + 4 <= 512, "barrier area");
+  static_assert((3 * C::NB + 2 * C::DB) * 8 + 4 <= 512, "barrier area");
 
   const int half = blockIdx.x % C::NH, worker = blockIdx.x / C::NH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +173,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       mbar_init(&empty[i], C::MC ? 2 : 1);   // multicast: both CTAs of the cluster write into a stage
       mbar_init(&sfull[i], C::LIVE_WARPS);
     }
-    for (int i = 0; i < kE2DBufs; ++i) {
+    for (int i = 0; i < C::DB; ++i) {
       mbar_init(&dfull[i], 1);
       mbar_init(&dempty[i], C::LIVE_WARPS);
     }
@@ -115,6 +188,20 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   const uint32_t tmem_base = *tmem_slot;
   if (warp >= kE2FirstEpiWarp && warp < kE2FirstEpiWarp + 4)
     load_weights_to_tmem<H>(Wp + (size_t)half * 2 * kM * H, tmem_base, warp & 3, lane);
+  if (kResidual && threadIdx.x < kM) {
+    // row r of the identity block: 1.0 at input channel r (if this CTA has that many), in the 128-byte swizzle
+    const int r = threadIdx.x;
+#pragma unroll
+    for (int kb = 0; kb < C::HC / kKB; ++kb) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (r < C::HC && (r >> 6) == kb && ((r & 63) >> 3) == j) w[(r & 7) >> 1] = (r & 1) ? 0x3C000000u : 0x00003C00u;
+        *reinterpret_cast<uint4*>(ident + kb * C::ID_KB_BYTES + r * 128 + ((j ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -179,13 +266,16 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     // ---------------------------------------------------------------- MMA issue
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
-      const int s = i % C::NB, d = i % kE2DBufs;
+      const int s = i % C::NB, d = i % C::DB;
       mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbFull), s, i);
-      mbar_wait(&dempty[d], ((i / kE2DBufs) & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbDEmpty), d, i);
+      mbar_wait(&dempty[d], ((i / C::DB) & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbDEmpty), d, i);
       tc_fence_after();
       if (elect_one()) {
-        issue_tile_mma_sw128<H, kE2NT>(tmem_base, tmem_base + C::D_COL0 + d * kE2NT,
-                                       smem_u32(bufs + (size_t)s * T::BUF_BYTES));
+        const uint32_t stage = smem_u32(bufs + (size_t)s * T::BUF_BYTES);
+        issue_tile_mma_sw128<H, kE2NT>(tmem_base, tmem_base + C::D_COL0 + d * kE2DCols, stage);
+        if (kResidual)
+          issue_ident_mma_sw128<C::HC, kE2NT>(tmem_base + C::D_COL0 + d * kE2DCols + kE2NT, smem_u32(ident),
+                                              stage + half * (C::HC / kKB) * T::KB_BYTES, T::IMG_BYTES, T::KB_BYTES);
         mma_commit(&dfull[d]);
       }
       __syncwarp();
@@ -259,15 +349,15 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     const bool ch_ok = cl < C::HC;           // warp-uniform (HC is a multiple of 32)
     const int c = half * C::HC + (ch_ok ? cl : 0);
     const int64_t my_tiles = ch_ok ? num_tiles : 0;   // warps without live channels (H = 64) sit the loop out
-    const float sc = scale_e[c], sh = shift_e[c];
     const char* Pc = reinterpret_cast<const char*>(P + 2 * c);        // (B1h[c], A2h[c]) interleaved
     const char* Pb2 = reinterpret_cast<const char*>(P + 2 * H + c);   // B2h[c]
     const int ldPb = (int)(ldP * (int64_t)sizeof(float));            // row pitch in bytes (< 2^31, checked by the host)
     constexpr unsigned kFull = 0xffffffffu;
-    // this thread's column of the stage: element (row, c) of an image sits at
-    //   (c / 64) * KB_BYTES + row * 128 + ((((c % 64) / 8) ^ (row % 8)) * 16) + (c % 8) * 2
-    const uint32_t col_base = (uint32_t)((c >> 6) * T::KB_BYTES + sub * kE2Chunk * 128 + ((c & 7) << 1));
-    const uint32_t col_x = (uint32_t)((c & 63) >> 3);
+    // The warp's 32 channels cw .. cw + 31 of an image: element (row, ch) sits at
+    //   (ch / 64) * KB_BYTES + row * 128 + ((((ch % 64) / 8) ^ (row % 8)) * 16) + (ch % 8) * 2
+    const int cw = half * C::HC + q * 32;
+    const uint32_t kb_off = (uint32_t)((cw >> 6) * T::KB_BYTES);
+    const int cx0 = (cw & 63) >> 3;          // first of the warp's four 16-byte chunks of a row (0 or 4)
     // Hand a finished stage to the store warp: every live warp of the group arrives on the STAGE's sfull.  All
     // arrivals of the stage's previous use precede its store, its reload and hence the `full` phase this warp has
     // waited for, so a fast warp can never complete a phase on behalf of a slower one.
@@ -280,8 +370,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     int i = 0;
     for (int64_t t = worker; t < my_tiles; t += workers, ++i) {
       if (i % kE2Groups != grp) continue;
-      const int s = i % C::NB, d = i % kE2DBufs;
-      const uint32_t dpar = (i / kE2DBufs) & 1;
+      const int s = i % C::NB, d = i % C::DB;
+      const uint32_t dpar = (i / C::DB) & 1;
       const int64_t cs = t * kE2NT + sub * kE2Chunk;
       const bool live = cs < E;              // warp-uniform; false only for the second half of a ragged last tile
       const int n = live ? (int)((E - cs < kE2Chunk) ? (E - cs) : kE2Chunk) : 0;
@@ -312,8 +402,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (next_dst == last_dst) tail_dst = last_dst;
 
       const int64_t chunk = cs / kE2Chunk;
-      const uint32_t st_hi = smem_u32(bufs + (size_t)s * T::BUF_BYTES) + col_base;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + d * kE2NT + sub * kE2Chunk;
+      const uint32_t st_img = smem_u32(bufs + (size_t)s * T::BUF_BYTES) + kb_off;   // hi image, this warp's k block
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + d * kE2DCols + sub * kE2Chunk;
       int cur = -1;
       float num = 0.f, den = 0.f;
 
@@ -344,12 +434,6 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           }
         }
       };
-      // Stage address of row r of the chunk for this thread's channel: st_hi + r * 128 + (((c%64)/8 ^ r%8) << 4).
-      // rowx[w] covers rows = w (mod 4) of the current half-batch; it advances by 4 rows per half-batch, which
-      // flips bit 2 of the swizzle term (xor 64 bytes) on top of the 512-byte step.
-      uint32_t rowx[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) rowx[w] = st_hi + (uint32_t)(w * 128) + ((col_x ^ (uint32_t)w) << 4);
       auto compute = [&](auto full_tag, int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
         constexpr bool kFullChunk = decltype(full_tag)::value;   // all 32 edges exist: no per-edge validity tests
         // Two half-batches of four edges.  The shared-memory accesses are volatile asm statements, which the
@@ -357,49 +441,19 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         // four per-edge dependency chains in between interleave.
 #pragma unroll
         for (int hb = 0; hb < kEB; hb += 4) {
-          uint32_t zr[4];
+          uint32_t zr[4], er[4] = {0u, 0u, 0u, 0u};
           tmem_ld4(taddr + b * kEB + hb, zr);
-          float ein[4];
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            ein[w] = 0.f;
-            if (kResidual) {
-              const __half_raw hr{lds_u16(rowx[w])}, lr{lds_u16(rowx[w] + T::IMG_BYTES)};
-              ein[w] = (__half2float(__half(hr)) + __half2float(__half(lr))) * kWScale;
-            }
-          }
+          if (kResidual) tmem_ld4(taddr + kE2NT + b * kEB + hb, er);   // e / 16 = hi + lo, exact
           tmem_ld_wait();
-          if (b == kE2Chunk / kEB - 1 && hb == 4) {   // last read of this accumulator buffer: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&dempty[d]);
-          }
           float v[4], sg[4];
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const int u = hb + w;
-            v[w] = fmaxf(fmaf(__uint_as_float(zr[w]) + xa[u].x + xb[u], sc, sh), 0.f) + ein[w];
-            sg[w] = (kFullChunk || b * kEB + u < n) ? sigmoidf_fast(v[w]) : 0.f;
+            // scaled domain: v = e' / 16 (the norm affine is folded into D, B1h' and B2h' by the caller)
+            v[w] = fmaf(fmaxf(__uint_as_float(zr[w]) + xa[u].x + xb[u], 0.f), kXScale, __uint_as_float(er[w]));
+            sg[w] = (kFullChunk || b * kEB + u < n) ? sigmoid16f_fast(v[w]) : 0.f;
           }
-          // split fp16: two edges per packed conversion
-          uint32_t ph[2], pl[2];
-#pragma unroll
-          for (int w2 = 0; w2 < 2; ++w2) {
-            const float x0 = v[2 * w2] * kXScale, x1 = v[2 * w2 + 1] * kXScale;
-            const __half2 hh = __floats2half2_rn(x0, x1);
-            const float2 back = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
-            ph[w2] = *reinterpret_cast<const uint32_t*>(&hh);
-            pl[w2] = *reinterpret_cast<const uint32_t*>(&ll);
-          }
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            if (kFullChunk || b * kEB + hb + w < n) {
-              sts_u16(rowx[w], (uint16_t)((w & 1) ? (ph[w >> 1] >> 16) : (ph[w >> 1] & 0xffffu)));
-              sts_u16(rowx[w] + T::IMG_BYTES, (uint16_t)((w & 1) ? (pl[w >> 1] >> 16) : (pl[w >> 1] & 0xffffu)));
-            }
-            rowx[w] = (rowx[w] + 512u) ^ 64u;
-          }
+          tmem_st4(taddr + kE2NT + b * kEB + hb, v);   // e' / 16 over the residual it was computed from (same lane)
           const unsigned mb = (segmask >> (b * kEB + hb)) & 0xfu;
           if (mb == 0) {                 // warp-uniform: the four edges continue the running segment
 #pragma unroll
@@ -458,6 +512,39 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       } else {
         F[(int64_t)cur * H + c] = gate_div(num, den);
       }
+      // e' (fp32, scaled) sits in this warp's 32 TMEM lanes x 32 columns: read it back as fragments, split, and store
+      // transposed into the stage: edge row T, channels cw + 16 hl + 8 a + [0, 8) = one 16-byte swizzle chunk
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      {
+        const uint32_t row = st_img + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          uint32_t fr[16];
+          tmem_ld_frag16x32(taddr + kE2NT + ((uint32_t)(hl * 16) << 16), fr);
+          tmem_ld_wait();
+          if (hl == 1) {   // last read of this accumulator set: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dempty[d]);
+          }
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            uint32_t fh[4], fl[4];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {   // edge block cb: edges 8 cb + 2 (T % 4), + 1 of channel T / 4 + 8 a
+              const float x0 = __uint_as_float(fr[4 * cb + 2 * a]), x1 = __uint_as_float(fr[4 * cb + 2 * a + 1]);
+              const __half2 hh = __floats2half2_rn(x0, x1);
+              const float2 back = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
+              fh[cb] = *reinterpret_cast<const uint32_t*>(&hh);
+              fl[cb] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            const uint32_t addr = row + ((((uint32_t)(cx0 + 2 * hl + a)) ^ ((uint32_t)lane & 7u)) << 4);
+            stmatrix_x4_trans(addr, fh[0], fh[1], fh[2], fh[3]);
+            stmatrix_x4_trans(addr + T::IMG_BYTES, fl[0], fl[1], fl[2], fl[3]);
+          }
+        }
+      }
       // e' is in the stage: make it visible to the async proxy, then hand the stage to the store warp
       fence_proxy_async();
       stage_done(s);
@@ -484,8 +571,7 @@ static int g_store_delay_ns = 0;
 
 template <int H>
 static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t ldP, const void* Wp,
-                                 const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
-                                 int flags, cudaStream_t stream) {
+                                 void* e16, float* F, float* carry, int flags, cudaStream_t stream) {
   using C = Edge2Cfg<H>;
   const bool res = flags & GNB_F_RESIDUAL;
   auto kern = g_edge_timing ? (res ? edge_forward_tc2_kernel<H, true, true> : edge_forward_tc2_kernel<H, false, true>)
@@ -514,7 +600,7 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  err = cudaLaunchKernelEx(&cfg, kern, map_e, *g, P, ldP, (const __half*)Wp, scale_e, shift_e, F, carry, flags, workers,
+  err = cudaLaunchKernelEx(&cfg, kern, map_e, *g, P, ldP, (const __half*)Wp, F, carry, flags, workers,
                            g_edge_timing, watch_get(), g_store_delay_ns);
   if (err != cudaSuccess) {
     set_error("gnb_edge_forward_tc2: launch failed: %s", cudaGetErrorString(err));
@@ -537,21 +623,20 @@ extern "C" void gnb_debug_edge_timing(void* buf) { tc::g_edge_timing = (unsigned
 extern "C" void gnb_debug_store_delay_ns(int ns) { tc::g_store_delay_ns = ns; }
 
 extern "C" int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
-                                    const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
-                                    int flags, void* stream) {
+                                    void* e16, float* F, float* carry, int flags, void* stream) {
   GNB_REQUIRE(g != nullptr && g->num_edges >= 0 && g->in_ptr != nullptr, "graph not staged");
   if (g->num_edges == 0) return 0;
   GNB_REQUIRE(g->in_src && g->in_dst, "graph not staged");
-  GNB_REQUIRE(P && Wp && scale_e && shift_e && e16 && F && carry, "null pointer");
+  GNB_REQUIRE(P && Wp && e16 && F && carry, "null pointer");
   GNB_REQUIRE(ldP >= ((flags & GNB_F_SYMMETRIC) ? 5 : 4) * (int64_t)H && ldP % 2 == 0 && ldP < ((int64_t)1 << 29),
               "ldP=%lld out of range", (long long)ldP);
   GNB_REQUIRE(((uintptr_t)P % 8 == 0) && ((uintptr_t)e16 % 16 == 0) && ((uintptr_t)Wp % 16 == 0),
               "gnb_edge_forward_tc2: e16 must be 16-byte aligned, P 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   switch (H) {
-    case 64: return tc::edge_forward_tc2_impl<64>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, flags, s);
-    case 128: return tc::edge_forward_tc2_impl<128>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, flags, s);
-    case 256: return tc::edge_forward_tc2_impl<256>(g, P, ldP, Wp, scale_e, shift_e, e16, F, carry, flags, s);
+    case 64: return tc::edge_forward_tc2_impl<64>(g, P, ldP, Wp, e16, F, carry, flags, s);
+    case 128: return tc::edge_forward_tc2_impl<128>(g, P, ldP, Wp, e16, F, carry, flags, s);
+    case 256: return tc::edge_forward_tc2_impl<256>(g, P, ldP, Wp, e16, F, carry, flags, s);
   }
   set_error("gnb_edge_forward_tc2: hidden_features=%d unsupported (64, 128, 256)", H);
   return GNB_E_INVALID;

@@ -107,11 +107,6 @@ class _GatedGCNBase(nn.Module):
         blocks_b.append(b(self.A_1))
         Wn = torch.cat(blocks_w, dim=0).contiguous()                 # [5H or 4H][H_in] (nn.Linear layout)
         bn = torch.cat(blocks_b, dim=0).contiguous()
-        if effective_backend(H) == 'tc2':
-            Wn_t, We_t = ops.pack_linear_tc(Wn), ops.pack_linear_tc(w(self.B_3).contiguous())
-        else:
-            Wn_t = Wn.t().contiguous()                               # k-major [H_in][5H or 4H]
-            We_t = w(self.B_3).t().contiguous()                      # k-major [H_in][H]
         if self.normalization == 'batch':
             se, te = _bn_affine(self.bn_e, device)
             sh, th = _bn_affine(self.bn_h, device)
@@ -120,6 +115,19 @@ class _GatedGCNBase(nn.Module):
                                       f"CUDA path so far")
         te = te + se * self.B_3.bias.detach().double().to(device)
         f32 = lambda t: t.to(torch.float32).contiguous()
+        if effective_backend(H) == 'tc2':
+            # gnb_edge_forward_tc2 takes the edge norm folded into its operands (fp64 here, rounded once):
+            #   bn_e(B1h[s] + B2h[d] + B_3 e) = (se * B1h)[s] + (se * B2h + te)[d] + (diag(se) B_3) e
+            Wn64, bn64, W364 = Wn.double(), bn.double(), w(self.B_3).double()
+            Wn64[0:2 * H:2] *= se[:, None]                           # B_1 rows of the interleaved (B1, A2) block
+            bn64[0:2 * H:2] *= se
+            Wn64[2 * H:3 * H] *= se[:, None]                         # B_2 block
+            bn64[2 * H:3 * H] = bn64[2 * H:3 * H] * se + te
+            Wn_t, We_t = ops.pack_linear_tc(f32(Wn64)), ops.pack_linear_tc(f32(W364 * se[:, None]))
+            bn = f32(bn64)
+        else:
+            Wn_t = Wn.t().contiguous()                               # k-major [H_in][5H or 4H]
+            We_t = w(self.B_3).t().contiguous()                      # k-major [H_in][H]
         return dict(Wn_t=Wn_t, bn=bn, We_t=We_t, scale_e=f32(se), shift_e=f32(te), scale_h=f32(sh), shift_h=f32(th))
 
     # -- position-order fast path (what the processor / model use) -----------------------------
@@ -186,7 +194,7 @@ class _GatedGCNBase(nn.Module):
             h16_out = torch.empty_like(h16)
         flags = self._flags()
         ops.node_linear_tc2(h16, pk['Wn_t'], pk['bn'], n_blocks * H, out=P)
-        ops.edge_forward_tc2(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e16, Fb, carry, flags)
+        ops.edge_forward_tc2(gi, H, P, pk['We_t'], e16, Fb, carry, flags)
         ops.node_update2(gi, H, P, e16, Fb, carry, h32, pk['scale_h'], pk['shift_h'], h_out, h16_out, flags,
                          gi.chunk(H, 'tc2'))
         ws['h_spare'], ws['h16_spare'] = h32, h16   # ping-pong: the caller no longer needs the inputs

@@ -243,11 +243,12 @@ def node_linear_tc2(x16, Wp, bias, M, out=None):
     return out
 
 
-def edge_forward_tc2(gi: GraphIndex, H, P, Wp, scale_e, shift_e, e16, F, carry, flags):
+def edge_forward_tc2(gi: GraphIndex, H, P, Wp, e16, F, carry, flags):
+    """The fused edge pass on the split16 state; the norm affine is folded into ``Wp`` and the B1h / B2h blocks of
+    ``P`` by the caller (see the header)."""
     lib = _lib.load()
     with _logged('gnb_edge_forward_tc2', e16.device):
-        _lib.check(lib.gnb_edge_forward_tc2(gi.ref(), H, _f32(P, 'P'), P.stride(0), Wp.data_ptr(),
-                                            _f32(scale_e, 'scale_e'), _f32(shift_e, 'shift_e'), _img(e16, 'e16'),
+        _lib.check(lib.gnb_edge_forward_tc2(gi.ref(), H, _f32(P, 'P'), P.stride(0), Wp.data_ptr(), _img(e16, 'e16'),
                                             _f32(F, 'F'), _f32(carry, 'carry'), flags,
                                             current_stream_ptr(e16.device)), 'gnb_edge_forward_tc2')
 

@@ -175,8 +175,10 @@ class CudaKernels:
         return self.ops.gather_rows(table, idx, out=out)
 
     def edge_forward(self, gi, H, P, pk, e_pos, F, carry, flags):
-        fn = self.ops.edge_forward_tc2 if e_pos.dtype == torch.float16 else self.ops.edge_forward
-        fn(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, F, carry, flags)
+        if e_pos.dtype == torch.float16:
+            self.ops.edge_forward_tc2(gi, H, P, pk['We_t'], e_pos, F, carry, flags)
+        else:
+            self.ops.edge_forward(gi, H, P, pk['We_t'], pk['scale_e'], pk['shift_e'], e_pos, F, carry, flags)
 
     def _family(self, H):
         return 'tc2' if self._split(H) else 'ffma'

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 9
+#define GNB_ABI_VERSION 10
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -191,13 +191,16 @@ int gnb_node_linear_tc2(const void* X16, int64_t rows, int K, const void* Wp, co
 int gnb_edge_tile_tc2(int H);
 int gnb_edge_chunk_tc2(int H);
 
-/* Tensor-core edition of gnb_edge_forward (gated_gcn_full.py:97,104-114): same contract, with the edge state e16 in
- * split16 format (updated in place), the edge weight given as gnb_pack_linear_tc(B_3.weight [H][H]) and carry sized
- * ceil(E / gnb_edge_chunk_tc2(H)) x 4 x H.  H in {64, 128, 256}; for H = 256 the two 128-channel halves of a tile
- * run on the two CTAs of a cluster that share the tile through TMA multicast. */
+/* Tensor-core edition of gnb_edge_forward (gated_gcn_full.py:97,104-114) with the edge state e16 in split16 format
+ * (updated in place) and carry sized ceil(E / gnb_edge_chunk_tc2(H)) x 4 x H.  The eval-mode norm affine is FOLDED
+ * INTO THE OPERANDS by the caller, so the kernel has no scale / shift arguments:
+ *   Wp = gnb_pack_linear_tc(diag(scale_e) * B_3.weight),   P[.][B1h block] = scale_e * B1h,
+ *   P[.][B2h block] = scale_e * B2h + shift_e  (shift_e includes scale_e * b_B3);  the A2h / A3h / A1h blocks unchanged.
+ *   e'_p = relu(e_p * Wp^T + P[src_p][B1h] + P[dst_p][B2h]) (+ e_p if GNB_F_RESIDUAL), F and carry as gnb_edge_forward.
+ * H in {64, 128, 256}; for H = 256 the two 128-channel halves of a tile run on the two CTAs of a cluster that share
+ * the tile through TMA multicast. */
 int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
-                         const float* scale_e, const float* shift_e, void* e16, float* F, float* carry,
-                         int flags, void* stream);
+                         void* e16, float* F, float* carry, int flags, void* stream);
 
 /* Debugging aid: buf = device uint64[SMs][32 warps][5] (or NULL to switch off); every epilogue warp of
  * gnb_edge_forward_tc2 then leaves its cycle accounting there (full wait, accumulator wait, compute, hand-off, tiles). */

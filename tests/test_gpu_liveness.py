@@ -29,7 +29,7 @@ def _model_and_graph(gnb, n, m, H, L=3, seed=5):
     return model, gnb.GraphIndex(src, dst, n), x.cuda(), e.cuda()
 
 
-@pytest.mark.parametrize('H,n,m', [(256, 60_000, 360_003), (128, 30_000, 180_001), (64, 30_000, 180_030)])
+@pytest.mark.parametrize('H,n,m', [(256, 60_000, 360_002), (128, 30_000, 180_002), (64, 30_000, 180_030)])
 @pytest.mark.parametrize('delay_ns', [3_000, 40_000])
 def test_edge_kernel_survives_a_stalled_store_thread(H, n, m, delay_ns):
     import gnnome_b200 as gnb

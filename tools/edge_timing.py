@@ -27,7 +27,7 @@ with torch.no_grad():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pk = conv._pack(e16.device)
     ev0.record()
-    ops.edge_forward_tc2(gi, H, ws['P'], pk['We_t'], pk['scale_e'], pk['shift_e'], e16, ws['F'], ws['carry'], conv._flags())
+    ops.edge_forward_tc2(gi, H, ws['P'], pk['We_t'], e16, ws['F'], ws['carry'], conv._flags())
     ev1.record()
     torch.cuda.synchronize()
     lib.gnb_debug_edge_timing(None)
