@@ -81,17 +81,19 @@ class _GatedGCNBase(nn.Module):
     def _flags(self):
         return (_lib.GNB_F_SYMMETRIC if self._symmetric else 0) | (_lib.GNB_F_RESIDUAL if self.residual else 0)
 
-    def _pack(self, device):
-        """Kernel-side views of the parameters (see _pack_now), cached until a parameter / buffer
-        changes (torch bumps ``_version`` on every in-place update) or moves."""
+    def _pack(self, device, family=None):
+        """Kernel-side views of the parameters for one kernel family ('tc2' / 'ffma', see _pack_now), cached until a
+        parameter / buffer changes (torch bumps ``_version`` on every in-place update) or moves."""
+        family = family or effective_backend(self.out_channels)
         key = tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers()))
-        key += (str(device), effective_backend(self.out_channels))
-        cache = self.__dict__.get('_pack_cache')
-        if cache is None or cache[0] != key:
-            cache = self.__dict__['_pack_cache'] = (key, self._pack_now(device))
-        return cache[1]
+        key += (str(device),)
+        cache = self.__dict__.setdefault('_pack_cache', {})
+        hit = cache.get(family)
+        if hit is None or hit[0] != key:
+            hit = cache[family] = (key, self._pack_now(device, family))
+        return hit[1]
 
-    def _pack_now(self, device):
+    def _pack_now(self, device, family):
         """The concatenated node projection with the (B1, A2) rows interleaved per channel, the
         edge projection, and the eval-mode norm affines (b_B3 folded into the edge shift)."""
         H = self.out_channels
@@ -115,7 +117,7 @@ class _GatedGCNBase(nn.Module):
                                       f"CUDA path so far")
         te = te + se * self.B_3.bias.detach().double().to(device)
         f32 = lambda t: t.to(torch.float32).contiguous()
-        if effective_backend(H) == 'tc2':
+        if family == 'tc2':
             # gnb_edge_forward_tc2 takes the edge norm folded into its operands (fp64 here, rounded once):
             #   bn_e(B1h[s] + B2h[d] + B_3 e) = (se * B1h)[s] + (se * B2h + te)[d] + (diag(se) B_3) e
             Wn64, bn64, W364 = Wn.double(), bn.double(), w(self.B_3).double()
@@ -140,7 +142,7 @@ class _GatedGCNBase(nn.Module):
             raise NotImplementedError('in_channels != out_channels is not supported by the CUDA path')
         H = self.out_channels
         dev = h.device
-        pk = self._pack(dev)
+        pk = self._pack(dev, 'ffma')
         ws = ws if ws is not None else {}
         n_blocks = 5 if self._symmetric else 4
         P = ws.get('P')
@@ -173,7 +175,7 @@ class _GatedGCNBase(nn.Module):
             raise NotImplementedError('in_channels != out_channels is not supported by the CUDA path')
         H = self.out_channels
         dev = h32.device
-        pk = self._pack(dev)
+        pk = self._pack(dev, 'tc2')
         ws = ws if ws is not None else {}
         n_blocks = 5 if self._symmetric else 4
 

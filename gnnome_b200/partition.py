@@ -164,7 +164,7 @@ class CudaKernels:
         return (h[0] if isinstance(h, tuple) else h).shape[1]
 
     def layer_pack(self, conv):
-        return conv._pack(self.device)
+        return conv._pack(self.device, self._family(conv.out_channels))
 
     def node_linear_layer(self, pk, h, M, out):
         if isinstance(h, tuple):
