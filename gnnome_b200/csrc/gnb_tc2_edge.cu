@@ -216,28 +216,41 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (lane == 0 && t > 0) r[2] = g.in_dst[t * kE2NT - 1];
       if (lane == 1 && (t + 1) * kE2NT < E) r[2] = g.in_dst[(t + 1) * kE2NT];
     };
-    // Every node row is touched for the first time by SOME gather of the epilogue, and that one would wait for
-    // HBM; the producer knows the tile's endpoints two to three tile periods before the epilogue needs them, so
-    // it pulls this CTA's slices of the (B1h, A2h)[src] and B2h[dst] rows into L2 ahead of time.
-    auto prefetch_rows = [&](const int (&r)[3]) {
-      {
-        const int sj = r[0], dj = r[1];
-        {   // rows past a ragged end carry node 0: a harmless prefetch
-          const char* a = reinterpret_cast<const char*>(P + (int64_t)sj * ldP + 2 * half * C::HC);
+    // Every node row is touched for the first time by SOME gather of the epilogue, and that one waits for HBM --
+    // with 8 edges per batch nearly every batch contains such a row, so the epilogue ran at DRAM latency (ncu: five
+    // warps stalled on the long scoreboard per issue slot, L2 hit rate 53 %).  The producer therefore runs
+    // kPfTiles tiles (~10 us) AHEAD of its TMA loads on the index arrays and pulls this CTA's slices of the
+    // (B1h, A2h)[src] and B2h[dst] rows of those tiles into L2.  (Prefetching only the tile about to be loaded, as
+    // round 1 did, is one to two tile periods ahead of the gathers: about one DRAM latency, i.e. too late.)
+    constexpr int kPfTiles = 6;
+    auto prefetch_rows = [&](int sj, int dj) {   // rows past a ragged end carry node 0: a harmless prefetch
+      const char* a = reinterpret_cast<const char*>(P + (int64_t)sj * ldP + 2 * half * C::HC);
 #pragma unroll
-          for (int l = 0; l < C::HC * 8 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
-          const char* b = reinterpret_cast<const char*>(P + (int64_t)dj * ldP + 2 * H + half * C::HC);
+      for (int l = 0; l < C::HC * 8 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
+      const char* b = reinterpret_cast<const char*>(P + (int64_t)dj * ldP + 2 * H + half * C::HC);
 #pragma unroll
-          for (int l = 0; l < C::HC * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + l * 128));
-        }
-      }
+      for (int l = 0; l < C::HC * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + l * 128));
+    };
+    auto load_pf = [&](int64_t t, int& sj, int& dj) {
+      const int64_t p0 = t * kE2NT + lane;
+      const bool ok = t < num_tiles && p0 < E;
+      sj = ok ? g.in_src[p0] : 0;
+      dj = ok ? g.in_dst[p0] : 0;
     };
     int cur[3], nxt[3];
     if (worker < num_tiles) load_idx(worker, cur);
+    for (int k = 0; k < kPfTiles; ++k) {         // prologue: the first kPfTiles tiles of this worker
+      int sj, dj;
+      load_pf(worker + (int64_t)k * workers, sj, dj);
+      if (worker + (int64_t)k * workers < num_tiles) prefetch_rows(sj, dj);
+    }
+    int pf_s, pf_d;                              // endpoints of tile i + kPfTiles, loaded one iteration before their use
+    load_pf(worker + (int64_t)kPfTiles * workers, pf_s, pf_d);
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
-      prefetch_rows(cur);
+      if (t + (int64_t)kPfTiles * workers < num_tiles) prefetch_rows(pf_s, pf_d);
+      load_pf(t + (int64_t)(kPfTiles + 1) * workers, pf_s, pf_d);
       mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkEdge2, kWrProducer, kWbEmpty), s, i);
       if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;

@@ -127,3 +127,48 @@ class EmulKernels:
         out = F.linear(torch.relu(F.linear(hid, d(pred.W2.weight), d(pred.W2.bias))), d(pred.W3.weight), d(pred.W3.bias))
         scores[gi.in_eid] = out.to(scores.dtype)
         return scores
+
+
+class TorchPrims:
+    """TEST INFRASTRUCTURE: plain-torch (autograd-native) implementation of the contracts
+    ``gnnome_b200.train_dist.CudaPrims`` offers, so that the CPU ``gloo`` tests can check the distributed logic of the
+    sharded training step (statistics, exchanges and their adjoints, loss scaling, gradient reduction)."""
+
+    def stage(self, src_local, dst_local, n_local):
+        return _Graph(src_local.cpu(), dst_local.cpu(), n_local)
+
+    def position_eids(self, gi):
+        return gi.in_eid
+
+    def dst_positions(self, gi):
+        return gi.dst
+
+    def gather_add3(self, gi, A_, B_, C_):
+        return A_.index_select(0, gi.src) + B_.index_select(0, gi.dst) + C_
+
+    def agg_in(self, gi, A_, sigma):
+        z = lambda: torch.zeros((gi.N, sigma.shape[1]), dtype=sigma.dtype)  # noqa: E731
+        num = z().index_add(0, gi.dst, sigma * A_.index_select(0, gi.src))
+        den = z().index_add(0, gi.dst, sigma)
+        return num / (den + EPS)
+
+    def seg_sum_out(self, gi, X):
+        return torch.zeros((gi.N, X.shape[1]), dtype=X.dtype).index_add(0, gi.src, X)
+
+    def gate(self, ehat, e_in):
+        e_new = torch.relu(ehat) if e_in is None else torch.relu(ehat) + e_in
+        return e_new, torch.sigmoid(e_new)
+
+    def col_stats(self, a, b=None, shift_a=None, shift_b=None):
+        a = a.double() - (0 if shift_a is None else shift_a.double())
+        b = a if b is None else b.double() - (0 if shift_b is None else shift_b.double())
+        return torch.stack((a.sum(0), (a * b).sum(0)))
+
+    def affine2(self, x, y, a, b, c, shift_x=None, shift_y=None):
+        out = a * (x.double() - (0 if shift_x is None else shift_x.double())) + c
+        if y is not None:
+            out = out + b * (y.double() - (0 if shift_y is None else shift_y.double()))
+        return out.to(x.dtype)
+
+    def layer_norm(self, norm, x):
+        return F.layer_norm(x, (x.shape[1],), norm.weight, norm.bias, norm.eps)
