@@ -41,7 +41,13 @@ WORKLOADS = {
     'cfg2s': (1_000_000, 6_000_000, 64, 8, 'synthetic 1M nodes / 6M edges, hidden=64 (shipped-model width), L=8'),
     'mid': (2_000_000, 12_000_000, 256, 8, 'synthetic 2M nodes / 12M edges, hidden=256, L=8 (profiling size)'),
     'small': (100_000, 600_000, 256, 8, 'synthetic 100k nodes / 600k edges, hidden=256, L=8 (debug size)'),
+    # training workloads (bench_train.py): one optimisation step = forward + BCE + backward + gradient all-reduce + Adam
+    'cfg5': (4_000_000, 24_000_000, 256, 8, 'train.py full forward+backward (BCE on edge scores), synthetic 4M nodes / 24M edges, hidden=256, L=8'),
+    'cfg5s': (500_000, 3_000_000, 256, 8, 'training step on the per-GPU share of config 5 at 8 GPUs: 0.5M nodes / 3M edges, hidden=256, L=8'),
+    'cfg5t': (50_000, 300_000, 256, 8, 'training step, debug size: 50k nodes / 300k edges, hidden=256, L=8'),
 }
+TRAIN_WORKLOADS = ('cfg5', 'cfg5s', 'cfg5t')
+CPU_TRAIN_SAMPLE = (10_000, 60_000)  # bounded sample for the CPU arm of the training workloads
 CPU_SAMPLE = (40_000, 240_000)      # bounded sample of the workload for the CPU arm (same H, L, generator)
 CPU_PASSES = 3                      # timed passes of the CPU arm inside the default GPU run (after one warm-up pass)
 if os.environ.get('GNB_BENCH_CPU_SAMPLE'):   # tests shrink it
@@ -454,11 +460,14 @@ def main():
     args = ap.parse_args()
     _protect_stdout()
     wl = WORKLOADS[args.workload]
+    train = args.workload in TRAIN_WORKLOADS
+    if train:
+        import bench_train
     if args.impl == 'reference':
-        run_reference_arm(args, wl)
+        bench_train.run_reference_arm(args, wl, emit) if train else run_reference_arm(args, wl)
         return
     try:
-        run_gpu_arm(args, wl)
+        bench_train.run_gpu_arm(args, wl, emit) if train else run_gpu_arm(args, wl)
     except Exception as exc:   # noqa: BLE001 -- a CUDA error (e.g. the kernels' spin watchdog trapped): say so in the line
         import traceback
         traceback.print_exc()

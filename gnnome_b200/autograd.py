@@ -29,8 +29,9 @@ def _c(t):
 
 
 def _call(name, device, *args):
+    from .ops import _logged          # launch accounting (bench.py), device guard
     lib = _lib.load()
-    with torch.cuda.device(device):
+    with _logged(name, device):
         _lib.check(getattr(lib, name)(*args, current_stream_ptr(device)), name)
 
 

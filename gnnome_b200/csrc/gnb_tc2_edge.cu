@@ -1,5 +1,5 @@
-// Fused edge pass of one (Sym)GatedGCN layer, second generation: TMA-fed tcgen05 with the edge state held in the
-// split16 format (gnb_tma.cuh).  Reference layers/gated_gcn_full.py:97,104-114:
+// Fused edge pass of one (Sym)GatedGCN layer: TMA-fed tcgen05 with the edge state held in the split16 format
+// (gnb_tma.cuh).  Reference layers/gated_gcn_full.py:97,104-114:
 //   z_p  = B1h[src_p] + B2h[dst_p] + e_p * W_B3^T         (E x H x H product on tcgen05, fp16 hi/lo split, fp32 in TMEM)
 //   e'_p = relu(z_p * scale + shift) (+ e_p)               written over e in place
 //   F_i  = sum_{p: dst_p = i} sigmoid(e'_p) * A2h[src_p] / (sum_p sigmoid(e'_p) + 1e-6)
@@ -8,32 +8,44 @@
 // the scaled domain the split16 state is stored in.  The residual e/16 = hi + lo is read from TENSOR MEMORY too: a
 // second, identity product (A = I from shared memory, B = the stage's own k blocks of this CTA's channels) puts it
 // there in the accumulator layout, exactly (one product per output), instead of two 16-bit shared loads, two
-// conversions and two floating-point operations per element in the issue-bound epilogue.
+// conversions and two floating-point operations per element.
 //
 // Persistent CTAs, one per SM; a CTA owns HC = min(H, 128) output channels (H = 256: the two channel halves of a
-// tile run on neighbouring CTAs) with its W_B3 block resident in TMEM, and walks 32-edge tiles of the dst-sorted
-// edge array (six to eight stages in flight: one per epilogue group plus the tiles being loaded / multiplied ahead).
-// One shared-memory stage serves a tile through its whole life:
-//   TMA load (hi, lo images, 128B-swizzled)  ->  MMA B operand  ->  residual source for the epilogue  ->
-//   e' written over it in place (same thread, same address)  ->  TMA store back to HBM.
-//   warp 0      : producer: TMA loads (lane 0) + the tile's (src, dst) indices into the stage's index area
-//   warp 1      : MMA issue (one lane)
-//   warps 2, 3  : TMA stores, one thread for the even stages, one for the odd ones, polling (store whichever finished stage
-//                 group is ready, release the stage).  The hand-over barrier sfull is PER STAGE and each stage has ONE
-//                 store thread: the barrier's phases are consumed in sequence by a single waiter, and a stage
-//                 cannot be armed again before that waiter has stored it and released it for reloading.
-//   Every wait is bounded by the spin watchdog (gnb_tc.cuh): a lost phase traps with a record instead of spinning.
-//   warps 4..19 : epilogue, 4 groups x 4 TMEM lane quarters; group g takes tiles g, g+4, ... (one 32-edge chunk).
-//                 A thread owns ONE channel and walks its 32 consecutive edges: gathers of the (B1h, A2h) node
-//                 rows are coalesced across the warp, per-destination sums are register accumulators closed at
-//                 warp-uniform segment boundaries (no atomics, fixed summation order).  Segments that straddle
-//                 a 32-edge chunk leave partial sums in carry[chunk][4][H], resolved by gnb_node_update2.
-//                 e' goes back through TENSOR MEMORY: the thread writes its fp32 values over the residual columns of
-//                 the accumulator set (its own lane), and after the tile the warp reads its 32 lanes back in the
-//                 matrix-fragment layout (tcgen05.ld.16x256b: a thread then holds pairs of consecutive edges of one
-//                 channel), splits the pairs into fp16 (hi, lo) with packed conversions and stores 8 x 8 blocks
-//                 TRANSPOSED into the stage with stmatrix -- 16-byte rows of 8 channels in the 128-byte swizzle --
-//                 instead of two 16-bit shared stores and the lane extraction per element.
+// tile run on the two CTAs of a cluster that share the tile through TMA multicast) with its W_B3 block resident in
+// TMEM, and walks 32-edge tiles of the dst-sorted edge array.  Tile i of a CTA belongs to epilogue group i % 4.
+//
+//   warp 0      : producer.  TMA loads of the tile's operand images into input stage i % NB (the loads run NB tiles
+//                 ahead of the tensor core), the tile's (src, dst) indices into the group's index slot, L2 prefetch
+//                 of the node rows the epilogue will gather.
+//   warp 1      : MMA issue (one lane): 3 K/16 split products into the group's accumulator set + 2 HC/16 identity
+//                 products for the residual; the commit RELEASES THE INPUT STAGE -- nothing but the tensor core
+//                 reads a stage, so the load pipeline is as deep as the stage ring (with the in-place stage of
+//                 round 1 / 2a, held from load to store, four of five stages sat under the epilogue groups and a
+//                 third of the epilogue's time was spent waiting for the next tile: profiles/r02b).
+//   warps 4..19 : epilogue, 4 groups x 4 TMEM lane quarters.  A thread owns ONE channel and walks the tile's 32
+//                 edges: gathers of the (B1h', A2h) node rows are coalesced across the warp, per-destination sums
+//                 are register accumulators closed at warp-uniform segment boundaries (no atomics, fixed summation
+//                 order).  Segments that straddle a tile leave partial sums in carry[tile][4][H], resolved by
+//                 gnb_node_update2.  e' goes back through TENSOR MEMORY: the thread writes its fp32 values over the
+//                 residual columns of the accumulator set (its own lane), and after the tile the warp reads its 32
+//                 lanes back in the matrix-fragment layout (tcgen05.ld.16x256b: a thread then holds pairs of
+//                 consecutive edges of one channel), splits the pairs into fp16 (hi, lo) with packed conversions and
+//                 stores 8 x 8 blocks TRANSPOSED into the group's OUTPUT BUFFER with stmatrix -- 16-byte rows of 8
+//                 channels in the 128-byte swizzle the TMA store expects.
+//   warps 2, 3  : TMA stores, lane 0 of warp 2 for groups 0 and 1, lane 0 of warp 3 for groups 2 and 3, polling.
+//
+// Barriers.  Every barrier has ONE producer side and ONE consumer that sees each of its phases in sequence, and every
+// ring has back-pressure, so a parity wait can neither be satisfied by the phase before last nor miss a phase (the
+// round-1 dead-lock was a group completing two phases of an un-back-pressured hand-over barrier; profiles/r02a):
+//   full[NB]      TMA bytes                       -> MMA warp
+//   empty[NB]     MMA commit (both CTAs in a cluster: either multicast writes into the stage) -> producer
+//   ifull[4][2]   producer (indices published)    -> the group's warps; a slot is rewritten 8 tiles later, which the
+//                 chain  load(i+8) <- MMA(i+8-NB) issued after MMA(i+4) <- dempty: group done with tile i  allows (NB <= 4)
+//   dfull[4]      MMA commit                      -> the group's warps
+//   dempty[4]     the group's warps (last TMEM read of the tile) -> MMA warp
+//   ofull[4]      the group's warps (e' in the output buffer)    -> store thread
+//   oempty[4]     store thread (buffer read by the TMA engine)    -> the group's warps
+// Every wait is bounded by the spin watchdog (gnb_tc.cuh): a lost phase traps with a record instead of spinning.
 #include <type_traits>
 
 #include "gnb_tma.cuh"
@@ -44,38 +56,42 @@ namespace tc {
 constexpr int kE2NT = 32;        // edges per tile (MMA N) = edges per epilogue warp = carry granularity
 constexpr int kE2Chunk = kE2NT;
 constexpr int kE2Groups = 4;     // epilogue groups of four warps (one per TMEM lane quarter); group g takes tiles g, g+G, ...
-                                 // (five groups were measured slower: the schedulers are issue-bound, r01h)
-constexpr int kE2DCols = 2 * kE2NT;   // TMEM columns of one accumulator set: z (32 edges) | residual e/16 (32 edges)
+                                 // (five groups were measured slower, r01h)
+constexpr int kE2DCols = 2 * kE2NT;   // TMEM columns of one accumulator set: z (32 edges) | residual e/16, then e'/16
 constexpr int kE2FirstEpiWarp = 4;
 constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 4 * kE2Groups);
-constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[32], dst[32], prev_dst, next_dst (+ pad: stages stay 16-byte aligned)
+constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[32], dst[32], prev_dst, next_dst (+ pad)
+constexpr int kE2IdxSlots = 2;              // index slots per group (see ifull above)
 
 template <int H>
 struct Edge2Cfg {
   static constexpr int HC = H < kM ? H : kM;   // live channels per CTA
   static constexpr int NH = H / HC;            // channel halves (CTAs per tile)
   // H = 256: the two channel halves of a tile form a 2-CTA cluster; each loads half of the tile's boxes and
-  // multicasts them to both, so the e tile is read from L2 / HBM once, and no inter-CTA flag is needed for the
-  // in-place update (a CTA stores its channels only after ITS stage is complete, i.e. after every box of the tile
-  // has been read from global memory on behalf of both)
+  // multicasts them to both, so the e tile is read from L2 / HBM once.  Both read whole rows of e and each overwrites
+  // its own channels in global memory; no flag is needed: a CTA stores tile t only after its own epilogue, i.e. after
+  // its own stage of tile t was complete, which means every box of the tile had been read from global memory on
+  // behalf of both CTAs.
   static constexpr bool MC = NH == 2;
   using T = Tile2<H, kE2NT>;
-  // Stages: one per group in its epilogue plus two being loaded / multiplied ahead.
-  static constexpr int NB = (H >= 256) ? 5 : 8;
-  // accumulator sets in TMEM: one per epilogue group (H = 256: the weight images take half of the 512 columns).  The
-  // MMA of a group's next tile waits for its epilogue; the other three groups hide that.  Set d is used by group d
-  // only, so each of its barriers has one producer and one consumer that sees every phase in sequence.
-  static constexpr int DB = kE2Groups;
+  static constexpr int NB = (H >= 256) ? 3 : 4;          // input stages (NB <= 4: see ifull)
+  static_assert(NB <= 4, "index slot reuse distance");
   // the identity block [128 rows (TMEM lanes)][HC input channels] as a K-major SWIZZLE_128B A operand
   static constexpr int ID_KB_BYTES = kM * 128;
   static constexpr int ID_BYTES = (HC / kKB) * ID_KB_BYTES;
-  // epilogue warps of a group that own live channels (the others idle: they must not feed the barriers, or they
-  // would run ahead of the live ones and complete a phase early)
+  // output buffer of a group: this CTA's channels of a tile, (hi | lo) x k blocks x 32 rows x 128 bytes
+  static constexpr int OKB = HC / kKB;
+  static constexpr int OIMG_BYTES = OKB * T::KB_BYTES;
+  static constexpr int OBUF_BYTES = 2 * OIMG_BYTES;
+  // epilogue warps of a group that own live channels (the others idle: they must not feed the barriers)
   static constexpr int LIVE_WARPS = HC / 32;
-  static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + DB * kE2DCols);
+  // accumulator sets in TMEM: one per epilogue group (H = 256: the weight images take half of the 512 columns)
+  static constexpr uint32_t TMEM_COLS = pow2_cols(2 * T::W_COLS + kE2Groups * kE2DCols);
   static constexpr uint32_t D_COL0 = 2 * T::W_COLS;
-  static_assert(2 * T::W_COLS + DB * kE2DCols <= 512, "tensor memory budget");
-  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + ID_BYTES + 1024 + (size_t)NB * kE2IdxInts * 4 + 512;
+  static_assert(2 * T::W_COLS + kE2Groups * kE2DCols <= 512, "tensor memory budget");
+  static constexpr int NBARS = 2 * NB + kE2Groups * (kE2IdxSlots + 4);
+  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + ID_BYTES + (size_t)kE2Groups * OBUF_BYTES + 1024 +
+                                 (size_t)kE2Groups * kE2IdxSlots * kE2IdxInts * 4 + NBARS * 8 + 16;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -150,17 +166,19 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic on the shared array (an integer round-trip would demote every later
   // access through these pointers to generic loads)
-  uint8_t* bufs = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bufs = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [NB] input stages
   uint8_t* ident = bufs + (size_t)C::NB * T::BUF_BYTES;
-  int* idx_area = reinterpret_cast<int*>(ident + C::ID_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_area + C::NB * kE2IdxInts);
-  uint64_t* full = bars;                    // [NB] producer (TMA bytes + 32 index lanes) -> MMA, epilogue
-  uint64_t* empty = full + C::NB;           // [NB] store warp -> producer
-  uint64_t* dfull = empty + C::NB;          // [D]  MMA -> epilogue
-  uint64_t* dempty = dfull + C::DB;         // [D]  epilogue -> MMA
-  uint64_t* sfull = dempty + C::DB;         // [NB] epilogue (e' written into the stage) -> store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + C::NB);
-  static_assert((3 * C::NB + 2 * C::DB) * 8 + 4 <= 512, "barrier area");
+  uint8_t* obufs = ident + C::ID_BYTES;                                            // [G] output buffers
+  int* idx_area = reinterpret_cast<int*>(obufs + (size_t)kE2Groups * C::OBUF_BYTES);   // [G][2] index slots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_area + kE2Groups * kE2IdxSlots * kE2IdxInts);
+  uint64_t* full = bars;                                   // [NB]
+  uint64_t* empty = full + C::NB;                          // [NB]
+  uint64_t* ifull = empty + C::NB;                         // [G][2]
+  uint64_t* dfull = ifull + kE2Groups * kE2IdxSlots;       // [G]
+  uint64_t* dempty = dfull + kE2Groups;                    // [G]
+  uint64_t* ofull = dempty + kE2Groups;                    // [G]
+  uint64_t* oempty = ofull + kE2Groups;                    // [G]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty + kE2Groups);
 
   const int half = blockIdx.x % C::NH, worker = blockIdx.x / C::NH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,20 +187,22 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::NB; ++i) {
-      mbar_init(&full[i], 33);
+      mbar_init(&full[i], 1);
       mbar_init(&empty[i], C::MC ? 2 : 1);   // multicast: both CTAs of the cluster write into a stage
-      mbar_init(&sfull[i], C::LIVE_WARPS);
     }
-    for (int i = 0; i < C::DB; ++i) {
+    for (int i = 0; i < kE2Groups * kE2IdxSlots; ++i) mbar_init(&ifull[i], 32);
+    for (int i = 0; i < kE2Groups; ++i) {
       mbar_init(&dfull[i], 1);
       mbar_init(&dempty[i], C::LIVE_WARPS);
+      mbar_init(&ofull[i], C::LIVE_WARPS);
+      mbar_init(&oempty[i], 1);
     }
     fence_barrier_init();
     prefetch_tensormap(&map_e);
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  if (C::MC) cluster_sync_all();   // the peer's multicast must find initialised barriers
+  if (C::MC) cluster_sync_all();   // the peer's multicast / commit must find initialised barriers
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -216,41 +236,23 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (lane == 0 && t > 0) r[2] = g.in_dst[t * kE2NT - 1];
       if (lane == 1 && (t + 1) * kE2NT < E) r[2] = g.in_dst[(t + 1) * kE2NT];
     };
-    // Every node row is touched for the first time by SOME gather of the epilogue, and that one waits for HBM --
-    // with 8 edges per batch nearly every batch contains such a row, so the epilogue ran at DRAM latency (ncu: five
-    // warps stalled on the long scoreboard per issue slot, L2 hit rate 53 %).  The producer therefore runs
-    // kPfTiles tiles (~10 us) AHEAD of its TMA loads on the index arrays and pulls this CTA's slices of the
-    // (B1h, A2h)[src] and B2h[dst] rows of those tiles into L2.  (Prefetching only the tile about to be loaded, as
-    // round 1 did, is one to two tile periods ahead of the gathers: about one DRAM latency, i.e. too late.)
-    constexpr int kPfTiles = 6;
-    auto prefetch_rows = [&](int sj, int dj) {   // rows past a ragged end carry node 0: a harmless prefetch
-      const char* a = reinterpret_cast<const char*>(P + (int64_t)sj * ldP + 2 * half * C::HC);
+    // Every node row is touched for the first time by SOME gather of the epilogue, and that one would wait for
+    // HBM; the producer knows the tile's endpoints NB tile periods before the epilogue needs them, so it pulls
+    // this CTA's slices of the (B1h, A2h)[src] and B2h[dst] rows into L2 ahead of time.
+    auto prefetch_rows = [&](const int (&r)[3]) {
+      const char* a = reinterpret_cast<const char*>(P + (int64_t)r[0] * ldP + 2 * half * C::HC);
 #pragma unroll
       for (int l = 0; l < C::HC * 8 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
-      const char* b = reinterpret_cast<const char*>(P + (int64_t)dj * ldP + 2 * H + half * C::HC);
+      const char* b = reinterpret_cast<const char*>(P + (int64_t)r[1] * ldP + 2 * H + half * C::HC);
 #pragma unroll
       for (int l = 0; l < C::HC * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + l * 128));
     };
-    auto load_pf = [&](int64_t t, int& sj, int& dj) {
-      const int64_t p0 = t * kE2NT + lane;
-      const bool ok = t < num_tiles && p0 < E;
-      sj = ok ? g.in_src[p0] : 0;
-      dj = ok ? g.in_dst[p0] : 0;
-    };
     int cur[3], nxt[3];
     if (worker < num_tiles) load_idx(worker, cur);
-    for (int k = 0; k < kPfTiles; ++k) {         // prologue: the first kPfTiles tiles of this worker
-      int sj, dj;
-      load_pf(worker + (int64_t)k * workers, sj, dj);
-      if (worker + (int64_t)k * workers < num_tiles) prefetch_rows(sj, dj);
-    }
-    int pf_s, pf_d;                              // endpoints of tile i + kPfTiles, loaded one iteration before their use
-    load_pf(worker + (int64_t)kPfTiles * workers, pf_s, pf_d);
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
-      if (t + (int64_t)kPfTiles * workers < num_tiles) prefetch_rows(pf_s, pf_d);
-      load_pf(t + (int64_t)(kPfTiles + 1) * workers, pf_s, pf_d);
+      prefetch_rows(cur);
       mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkEdge2, kWrProducer, kWbEmpty), s, i);
       if (elect_one()) {
         uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
@@ -267,11 +269,12 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         }
       }
       if (t + workers < num_tiles) load_idx(t + workers, nxt);   // in flight while this tile's indices are published
-      int* ia = idx_area + s * kE2IdxInts;
+      const int grp = i % kE2Groups, slot = (i / kE2Groups) % kE2IdxSlots;
+      int* ia = idx_area + (grp * kE2IdxSlots + slot) * kE2IdxInts;
       ia[lane] = cur[0];
       ia[kE2NT + lane] = cur[1];
       if (lane < 2) ia[2 * kE2NT + lane] = cur[2];
-      mbar_arrive(&full[s]);
+      mbar_arrive(&ifull[grp * kE2IdxSlots + slot]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) cur[k] = nxt[k];
     }
@@ -279,9 +282,9 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     // ---------------------------------------------------------------- MMA issue
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
-      const int s = i % C::NB, d = i % C::DB;
+      const int s = i % C::NB, d = i % kE2Groups;
       mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbFull), s, i);
-      mbar_wait(&dempty[d], ((i / C::DB) & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbDEmpty), d, i);
+      mbar_wait(&dempty[d], ((i / kE2Groups) & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbDEmpty), d, i);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t stage = smem_u32(bufs + (size_t)s * T::BUF_BYTES);
@@ -289,66 +292,59 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         if (kResidual)
           issue_ident_mma_sw128<C::HC, kE2NT>(tmem_base + C::D_COL0 + d * kE2DCols + kE2NT, smem_u32(ident),
                                               stage + half * (C::HC / kKB) * T::KB_BYTES, T::IMG_BYTES, T::KB_BYTES);
-        mma_commit(&dfull[d]);
+        // the products have read the stage: hand it back to the producer(s) ...
+        if (C::MC) mma_commit_mc(&empty[s], (uint16_t)3);
+        else mma_commit(&empty[s]);
+        mma_commit(&dfull[d]);   // ... and the accumulators to the group
       }
       __syncwarp();
     }
   } else if (warp < kE2FirstEpiWarp) {
-    // ---------------------------------------------------------------- TMA store of one epilogue group
-    // Lane 0 of warp 2 stores the tiles that pass through the even stages, lane 0 of warp 3 those of the odd stages.
-    // A stage's hand-over barrier thus has ONE consumer that sees every phase of it in sequence: it tests phase k
-    // only after it has stored phase k - 1, and phase k + 1 cannot complete before it releases the stage -- the
-    // parity test can neither alias forwards nor be satisfied by the phase before last.  (Round 1 assigned the
-    // stores by epilogue GROUP with one barrier per group: a group could complete two phases while the thread was
-    // busy with its other group -- the cfg3 dead-lock.  One barrier per stage polled by the group's thread is wrong
-    // the other way round: with NB = 6 a stage alternates between two groups, so each thread saw every OTHER phase
-    // and a fresh barrier satisfied its parity test before the tile had even been processed.)
-    // The thread POLLS its stages without blocking on any of them (tiles of different groups finish out of order).
+    // ---------------------------------------------------------------- TMA stores
+    // Lane 0 of warp 2 stores the tiles of groups 0 and 1, lane 0 of warp 3 those of groups 2 and 3.  It POLLS its two
+    // groups without blocking on either (their tiles finish out of order).  A group cannot refill its output buffer
+    // before this thread has released it (oempty), so ofull never runs ahead of its one consumer.
     if (lane == 0) {
-      const int l0 = warp - 2;                              // stages l0, l0 + 2, ...
-      constexpr int kMaxSt = (C::NB + 1) / 2;
-      int it[kMaxSt];                                       // next tile iteration that passes through each served stage
+      constexpr int kPer = kE2Groups / 2;
+      const int g0 = (warp - 2) * kPer;
+      int it[kPer];                                        // next tile iteration of each served group
 #pragma unroll
-      for (int k = 0; k < kMaxSt; ++k) it[k] = l0 + 2 * k;
-      auto remaining = [&](int k) { return l0 + 2 * k < C::NB && worker + (int64_t)it[k] * workers < num_tiles; };
+      for (int k = 0; k < kPer; ++k) it[k] = g0 + k;
+      auto remaining = [&](int k) { return worker + (int64_t)it[k] * workers < num_tiles; };
       auto any_remaining = [&]() {
         bool r = false;
 #pragma unroll
-        for (int k = 0; k < kMaxSt; ++k) r = r || remaining(k);
+        for (int k = 0; k < kPer; ++k) r = r || remaining(k);
         return r;
       };
       SpinGuard guard;
       while (any_remaining()) {
         bool progressed = false;
 #pragma unroll
-        for (int k = 0; k < kMaxSt; ++k) {
+        for (int k = 0; k < kPer; ++k) {
           if (!remaining(k)) continue;
-          const int i = it[k];
-          const int s = l0 + 2 * k;                         // == i % NB
-          if (!mbar_test(&sfull[s], (i / C::NB) & 1)) continue;
+          const int i = it[k], grp = g0 + k;
+          if (!mbar_test(&ofull[grp], (i / kE2Groups) & 1)) continue;
           const int64_t t = worker + (int64_t)i * workers;
-          const uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
+          const uint8_t* ob = obufs + (size_t)grp * C::OBUF_BYTES;
 #pragma unroll
-          for (int kbl = 0; kbl < C::HC / kKB; ++kbl) {
-            const int kb = half * (C::HC / kKB) + kbl;
-            tma_store_2d(&map_e, stage + kb * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
-            tma_store_2d(&map_e, stage + T::IMG_BYTES + kb * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT));
+          for (int kbl = 0; kbl < C::OKB; ++kbl) {
+            const int kb = half * C::OKB + kbl;
+            tma_store_2d(&map_e, ob + kbl * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
+            tma_store_2d(&map_e, ob + C::OIMG_BYTES + kbl * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT));
           }
           tma_store_commit();
           tma_store_wait_read();
           if (store_delay_ns > 0) __nanosleep((unsigned)store_delay_ns);   // fault injection (gnb_debug_store_delay_ns)
-          if (store_delay_ns >= 0) {   // < 0: the stage is never released -- the watchdog test's dead-lock
-            mbar_arrive(&empty[s]);
-            if (C::MC) mbar_arrive_cluster(&empty[s], (uint32_t)(half ^ 1));   // the peer also writes into this stage
-          }
-          it[k] += C::NB;
+          if (store_delay_ns >= 0) mbar_arrive(&oempty[grp]);   // < 0: never released -- the watchdog test's dead-lock
+          it[k] += kE2Groups;
           progressed = true;
         }
         if (progressed) {
           guard = SpinGuard();
         } else {
           __nanosleep(32);
-          guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbSFull), (uint32_t)l0, (uint32_t)((it[0] / C::NB) & 1), it[0]);
+          guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbSFull), (uint32_t)g0, (uint32_t)((it[0] / kE2Groups) & 1), it[0]);
         }
       }
       tma_store_wait_all();
@@ -357,52 +353,34 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     // ---------------------------------------------------------------- epilogue
     const int ew = warp - kE2FirstEpiWarp;
     const int grp = ew >> 2, q = warp & 3;
-    constexpr int sub = 0;                   // one 32-edge chunk per tile
     const int cl = q * 32 + lane;            // TMEM lane = channel within the CTA's block
     const bool ch_ok = cl < C::HC;           // warp-uniform (HC is a multiple of 32)
     const int c = half * C::HC + (ch_ok ? cl : 0);
     const int64_t my_tiles = ch_ok ? num_tiles : 0;   // warps without live channels (H = 64) sit the loop out
-    const char* Pc = reinterpret_cast<const char*>(P + 2 * c);        // (B1h[c], A2h[c]) interleaved
-    const char* Pb2 = reinterpret_cast<const char*>(P + 2 * H + c);   // B2h[c]
+    const char* Pc = reinterpret_cast<const char*>(P + 2 * c);        // (B1h'[c], A2h[c]) interleaved
+    const char* Pb2 = reinterpret_cast<const char*>(P + 2 * H + c);   // B2h'[c]
     const int ldPb = (int)(ldP * (int64_t)sizeof(float));            // row pitch in bytes (< 2^31, checked by the host)
     constexpr unsigned kFull = 0xffffffffu;
-    // The warp's 32 channels cw .. cw + 31 of an image: element (row, ch) sits at
+    // The warp's 32 channels q * 32 .. + 31 of the CTA's block inside an output image: element (row, ch) sits at
     //   (ch / 64) * KB_BYTES + row * 128 + ((((ch % 64) / 8) ^ (row % 8)) * 16) + (ch % 8) * 2
-    const int cw = half * C::HC + q * 32;
-    const uint32_t kb_off = (uint32_t)((cw >> 6) * T::KB_BYTES);
-    const int cx0 = (cw & 63) >> 3;          // first of the warp's four 16-byte chunks of a row (0 or 4)
-    // Hand a finished stage to the store warp: every live warp of the group arrives on the STAGE's sfull.  All
-    // arrivals of the stage's previous use precede its store, its reload and hence the `full` phase this warp has
-    // waited for, so a fast warp can never complete a phase on behalf of a slower one.
-    // optional cycle accounting (gnb_debug_edge_timing): [full wait, dfull wait, batches, flush + hand-off, tiles]
+    const uint32_t ob_row = smem_u32(obufs + (size_t)grp * C::OBUF_BYTES) + (uint32_t)(((q * 32) >> 6) * T::KB_BYTES) +
+                            (uint32_t)lane * 128u;
+    const int cx0 = ((q * 32) & 63) >> 3;    // first of the warp's four 16-byte chunks of a row (0 or 4)
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + grp * kE2DCols;
+    // optional cycle accounting (gnb_debug_edge_timing): [index wait, accumulator wait, batches, pack + hand-off, tiles]
     unsigned long long tm[5] = {0, 0, 0, 0, 0};
-    auto stage_done = [&](int s) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[s]);
-    };
-    int i = 0;
-    for (int64_t t = worker; t < my_tiles; t += workers, ++i) {
-      if (i % kE2Groups != grp) continue;
-      const int s = i % C::NB, d = i % C::DB;
-      const uint32_t dpar = (i / C::DB) & 1;
-      const int64_t cs = t * kE2NT + sub * kE2Chunk;
-      const bool live = cs < E;              // warp-uniform; false only for the second half of a ragged last tile
-      const int n = live ? (int)((E - cs < kE2Chunk) ? (E - cs) : kE2Chunk) : 0;
+    int jj = 0;                              // tiles of this group so far
+    for (int64_t t = worker + (int64_t)grp * workers; t < my_tiles; t += (int64_t)kE2Groups * workers, ++jj) {
+      const int i = grp + kE2Groups * jj;
+      const int64_t cs = t * kE2NT;
+      const int n = (int)((E - cs < kE2Chunk) ? (E - cs) : kE2Chunk);
       const long long t0 = kTiming ? clock64() : 0;
-      // indices published (and the operand tile has landed)
-      mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbFull), s, i);
+      const int slot = jj % kE2IdxSlots;
+      mbar_wait(&ifull[grp * kE2IdxSlots + slot], (jj / kE2IdxSlots) & 1, 32, watch,
+                watch_tag(kWkEdge2, kWrEpilogue, kWbFull), grp * kE2IdxSlots + slot, i);
       const long long t1 = kTiming ? clock64() : 0;
-      if (!live) {  // nothing to compute, but the barriers still have to be fed
-        mbar_wait(&dfull[d], dpar, 64, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbDFull), d, i);
-        tc_fence_after();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dempty[d]);
-        stage_done(s);
-        continue;
-      }
-      const int* ia = idx_area + s * kE2IdxInts;
-      const int my_dst = ia[kE2NT + sub * kE2Chunk + lane];
+      const int* ia = idx_area + (grp * kE2IdxSlots + slot) * kE2IdxInts;
+      const int my_dst = ia[kE2NT + lane];
       const int prev_dst = ia[2 * kE2NT];
       const int next_dst = ia[2 * kE2NT + 1];
       int head_dst = -1, tail_dst = -1;
@@ -415,16 +393,14 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (next_dst == last_dst) tail_dst = last_dst;
 
       const int64_t chunk = cs / kE2Chunk;
-      const uint32_t st_img = smem_u32(bufs + (size_t)s * T::BUF_BYTES) + kb_off;   // hi image, this warp's k block
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::D_COL0 + d * kE2DCols + sub * kE2Chunk;
       int cur = -1;
       float num = 0.f, den = 0.f;
 
-      // Software pipeline over four batches of eight edges: the gathers of batch b+1 -- xa = (B1h, A2h)[src] and
-      // xb = B2h[dst], one coalesced row segment per warp each -- are in flight while batch b is computed.
+      // Software pipeline over four batches of eight edges: the gathers of batch b+1 -- xa = (B1h', A2h)[src] and
+      // xb = B2h'[dst], one coalesced row segment per warp each -- are in flight while batch b is computed.
       constexpr int kEB = 8;
-      const int* ia_src = ia + sub * kE2Chunk;            // endpoints of the chunk's 32 edges: warp-uniform reads
-      const int* ia_dst = ia + kE2NT + sub * kE2Chunk;
+      const int* ia_src = ia;                            // endpoints of the chunk's 32 edges: warp-uniform reads
+      const int* ia_dst = ia + kE2NT;
       auto fetch = [&](int b, float2 (&xa)[kEB], float (&xb)[kEB]) {
         int sj[kEB], dj[kEB];
         *reinterpret_cast<int4*>(&sj[0]) = *reinterpret_cast<const int4*>(ia_src + b * kEB);
@@ -433,7 +409,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         *reinterpret_cast<int4*>(&dj[4]) = *reinterpret_cast<const int4*>(ia_dst + b * kEB + 4);
 #pragma unroll
         for (int u = 0; u < kEB; ++u) xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj[u] * ldPb));
-        // B2h[dst]: the four edges of a quad share it unless a destination segment opens at its 2nd..4th edge
+        // B2h'[dst]: the four edges of a quad share it unless a destination segment opens at its 2nd..4th edge
         const unsigned m8 = segmask >> (b * kEB);
 #pragma unroll
         for (int hq = 0; hq < kEB; hq += 4) {
@@ -449,9 +425,6 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       };
       auto compute = [&](auto full_tag, int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
         constexpr bool kFullChunk = decltype(full_tag)::value;   // all 32 edges exist: no per-edge validity tests
-        // Two half-batches of four edges.  The shared-memory accesses are volatile asm statements, which the
-        // compiler keeps in program order: the loads of a half-batch come first and its stores last, so that the
-        // four per-edge dependency chains in between interleave.
 #pragma unroll
         for (int hb = 0; hb < kEB; hb += 4) {
           uint32_t zr[4], er[4] = {0u, 0u, 0u, 0u};
@@ -498,9 +471,9 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       };
       float2 fa0[kEB], fa1[kEB];
       float fb0[kEB], fb1[kEB];
-      fetch(0, fa0, fb0);
+      fetch(0, fa0, fb0);                                // in flight while the tile's products complete
       const long long t2 = kTiming ? clock64() : 0;
-      mbar_wait(&dfull[d], dpar, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbDFull), d, i);
+      mbar_wait(&dfull[grp], jj & 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbDFull), grp, i);
       tc_fence_after();
       const long long t3 = kTiming ? clock64() : 0;
       auto run_chunk = [&](auto full_tag) {
@@ -526,41 +499,41 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         F[(int64_t)cur * H + c] = gate_div(num, den);
       }
       // e' (fp32, scaled) sits in this warp's 32 TMEM lanes x 32 columns: read it back as fragments, split, and store
-      // transposed into the stage: edge row T, channels cw + 16 hl + 8 a + [0, 8) = one 16-byte swizzle chunk
+      // transposed into the group's output buffer: edge row T, channels 16 hl + 8 a + [0, 8) = one 16-byte swizzle chunk.
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      {
-        const uint32_t row = st_img + (uint32_t)lane * 128u;
+      // the buffer still holds the group's previous tile until the store thread has handed it back
+      mbar_wait(&oempty[grp], (jj & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbEmpty), grp, i);
 #pragma unroll
-        for (int hl = 0; hl < 2; ++hl) {
-          uint32_t fr[16];
-          tmem_ld_frag16x32(taddr + kE2NT + ((uint32_t)(hl * 16) << 16), fr);
-          tmem_ld_wait();
-          if (hl == 1) {   // last read of this accumulator set: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&dempty[d]);
+      for (int hl = 0; hl < 2; ++hl) {
+        uint32_t fr[16];
+        tmem_ld_frag16x32(taddr + kE2NT + ((uint32_t)(hl * 16) << 16), fr);
+        tmem_ld_wait();
+        if (hl == 1) {   // last read of this accumulator set: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dempty[grp]);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          uint32_t fh[4], fl[4];
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {   // edge block cb: edges 8 cb + 2 (T % 4), + 1 of channel T / 4 + 8 a
+            const float x0 = __uint_as_float(fr[4 * cb + 2 * a]), x1 = __uint_as_float(fr[4 * cb + 2 * a + 1]);
+            const __half2 hh = __floats2half2_rn(x0, x1);
+            const float2 back = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
+            fh[cb] = *reinterpret_cast<const uint32_t*>(&hh);
+            fl[cb] = *reinterpret_cast<const uint32_t*>(&ll);
           }
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            uint32_t fh[4], fl[4];
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {   // edge block cb: edges 8 cb + 2 (T % 4), + 1 of channel T / 4 + 8 a
-              const float x0 = __uint_as_float(fr[4 * cb + 2 * a]), x1 = __uint_as_float(fr[4 * cb + 2 * a + 1]);
-              const __half2 hh = __floats2half2_rn(x0, x1);
-              const float2 back = __half22float2(hh);
-              const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
-              fh[cb] = *reinterpret_cast<const uint32_t*>(&hh);
-              fl[cb] = *reinterpret_cast<const uint32_t*>(&ll);
-            }
-            const uint32_t addr = row + ((((uint32_t)(cx0 + 2 * hl + a)) ^ ((uint32_t)lane & 7u)) << 4);
-            stmatrix_x4_trans(addr, fh[0], fh[1], fh[2], fh[3]);
-            stmatrix_x4_trans(addr + T::IMG_BYTES, fl[0], fl[1], fl[2], fl[3]);
-          }
+          const uint32_t addr = ob_row + ((((uint32_t)(cx0 + 2 * hl + a)) ^ ((uint32_t)lane & 7u)) << 4);
+          stmatrix_x4_trans(addr, fh[0], fh[1], fh[2], fh[3]);
+          stmatrix_x4_trans(addr + C::OIMG_BYTES, fl[0], fl[1], fl[2], fl[3]);
         }
       }
-      // e' is in the stage: make it visible to the async proxy, then hand the stage to the store warp
+      // e' is in the output buffer: make it visible to the async proxy, then hand it to the store thread
       fence_proxy_async();
-      stage_done(s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ofull[grp]);
       if (kTiming) {
         const long long t5 = clock64();
         tm[0] += t1 - t0; tm[1] += t3 - t2; tm[2] += (t4 - t3) + (t2 - t1); tm[3] += t5 - t4; tm[4] += 1;

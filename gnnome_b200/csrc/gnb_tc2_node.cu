@@ -174,12 +174,10 @@ constexpr int kNu2Batch = 4;   // out-edges in flight per thread (64 bytes each)
 
 // H / 8 threads ("group") per node, 8 channels per thread: per out-edge a 16-byte hi + 16-byte lo load of the e'
 // row (one contiguous 4H-byte row per group) and a 32-byte load of A3h[dst].  Latency is what bounds this kernel
-// (CSR pointers -> edge indices -> rows are dependent loads), so the chain is software-pipelined across the group's
-// nodes: the pointers are fetched TWO nodes ahead and the edge indices (position, destination) of the first H / 8
-// out-edges ONE node ahead, so that a node's row loads are issued the moment its turn comes (with only the
-// pointers prefetched a node cost two dependent memory latencies and the kernel ran at ~60 % of the HBM peak with
-// 7 warps stalled on a load per issue slot); everything that depends only on the node id is issued before the
-// edge loop, the indices are broadcast by shuffle, and four edge rows are in flight per thread.
+// (CSR pointers -> edge indices -> rows are dependent loads), so: the pointers of the group's NEXT node are
+// fetched one iteration ahead, everything that depends only on the node id is issued before the edge loop, the
+// group loads the indices of up to H / 8 edges with one instruction and broadcasts them by shuffle, and four
+// edge rows are in flight per thread.
 template <int H>
 __global__ void __launch_bounds__(kNu2Threads, 2)
 node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ e16,
@@ -198,26 +196,16 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
   const unsigned gmask = TPN >= 32 ? 0xffffffffu : (((1u << TPN) - 1u) << (((threadIdx.x & 31) / TPN) * TPN));
   const int64_t stride = (int64_t)gridDim.x * NPB;
   int64_t i = node_begin + (int64_t)blockIdx.x * NPB + slot;
-  int qa = 0, qb = 0, pa = 0, pb = 0;         // CSR pointers of the current node ...
-  int nqa = 0, nqb = 0;                       // ... out-edge pointers of this group's next node
-  int myp = 0, myd = 0;                       // position / destination of out-edge qa + t of the current node
+  int qa = 0, qb = 0, pa = 0, pb = 0;
   if (i < node_end) {
     if (agg) { qa = g.out_ptr[i]; qb = g.out_ptr[i + 1]; }
     if (!partial_out) { pa = g.in_ptr[i]; pb = g.in_ptr[i + 1]; }
   }
-  if (agg && i + stride < node_end) { nqa = g.out_ptr[i + stride]; nqb = g.out_ptr[i + stride + 1]; }
-  if (agg && t < qb - qa) {
-    myp = g.out_pos[qa + t];
-    myd = g.out_dst[qa + t];
-  }
   for (; i < node_end; i += stride) {
-    int fqa = 0, fqb = 0, npa = 0, npb = 0;   // out-edge pointers two nodes ahead, indices and in-edge pointers one ahead
-    if (agg && i + 2 * stride < node_end) { fqa = g.out_ptr[i + 2 * stride]; fqb = g.out_ptr[i + 2 * stride + 1]; }
-    if (!partial_out && i + stride < node_end) { npa = g.in_ptr[i + stride]; npb = g.in_ptr[i + stride + 1]; }
-    int nmyp = 0, nmyd = 0;
-    if (agg && t < nqb - nqa) {
-      nmyp = g.out_pos[nqa + t];
-      nmyd = g.out_dst[nqa + t];
+    int nqa = 0, nqb = 0, npa = 0, npb = 0;   // CSR pointers of this group's next node: one iteration ahead
+    if (i + stride < node_end) {
+      if (agg) { nqa = g.out_ptr[i + stride]; nqb = g.out_ptr[i + stride + 1]; }
+      if (!partial_out) { npa = g.in_ptr[i + stride]; npb = g.in_ptr[i + stride + 1]; }
     }
     // ---- everything that depends on the node id only ------------------------------------------------
     F8 a1 = f8_zero(), hin = f8_zero(), f = f8_zero();
@@ -233,7 +221,8 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       F8 num = f8_zero(), den = f8_zero();
       for (int q0 = qa; q0 < qb; q0 += TPN) {
         const int cnt = (qb - q0 < TPN) ? (qb - q0) : TPN;   // group-uniform
-        if (q0 > qa && t < cnt) {   // the first H / 8 edges were fetched one node ahead
+        int myp = 0, myd = 0;
+        if (t < cnt) {
           myp = g.out_pos[q0 + t];
           myd = g.out_dst[q0 + t];
         }
@@ -266,7 +255,7 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       if (partial_out) {  // multi-GPU: un-normalised partial sums of a halo source node, for its owner
         f8_store(partial_out + (i - node_begin) * 2 * H + c0, num);
         f8_store(partial_out + (i - node_begin) * 2 * H + H + c0, den);
-        qa = nqa; qb = nqb; nqa = fqa; nqb = fqb; myp = nmyp; myd = nmyd;
+        qa = nqa; qb = nqb;
         continue;
       }
       if (xp_ptr) {       // multi-GPU: partial sums other ranks computed for this node, in rank order
@@ -315,8 +304,6 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       *reinterpret_cast<uint4*>(h16_out + (i - node_begin) * 2 * H + H + c0) = ll;
     }
     qa = nqa; qb = nqb; pa = npa; pb = npb;
-    nqa = fqa; nqb = fqb;
-    myp = nmyp; myd = nmyd;
   }
 }
 
