@@ -237,3 +237,40 @@ def test_training_step_vs_oracle_autograd(gnb, kind, norm):
             assert int(b) == int(p[k]), k
         else:
             torch.testing.assert_close(b.cpu(), p[k].detach(), rtol=1e-4, atol=1e-5, msg=k)
+
+
+@pytest.mark.parametrize('kind', ['sym', 'gated'])
+def test_sharded_trainer_world1_matches_the_model_training_path(gnb, kind):
+    """gnnome_b200.train_dist.ShardedTrainer on one rank (CUDA primitives, layer check-pointing) against the model's own
+    train-mode forward + torch BCE + backward: same loss, same gradients, same BatchNorm buffers.  (The distributed logic
+    is checked on CPU by tests/test_train_dist.py; the oracle's autograd by the tests above.)"""
+    import copy
+    from gnnome_b200 import train_dist
+    n, m, H, L = 3000, 18000, 64, 3
+    src, dst = synth.make_assembly_graph(n, m, seed=21)
+    x, e = synth.make_features(src, dst, n, seed=21)
+    src, dst, x, e = map(torch.from_numpy, (src, dst, x, e))
+    y = (torch.rand(m, generator=torch.Generator().manual_seed(3)) < 0.75).float()
+    torch.manual_seed(9)
+    if kind == 'sym':
+        model = gnb.models.SymGatedGCNModel(2, 2, H, 16, L, 64, 'batch', dropout=None)
+    else:
+        model = gnb.models.GatedGCNModel(2, 2, H, 16, L, 64, 'batch', dropout=None, directed=True)
+    model = model.cuda().train()
+    ref = copy.deepcopy(model)
+    out = ref((src, dst, n), x.cuda(), e.cuda()).squeeze(-1)
+    ref_loss = F.binary_cross_entropy_with_logits(out, y.cuda(), pos_weight=torch.tensor(1 / 3, device='cuda'))
+    ref_loss.backward()
+    tr = train_dist.ShardedTrainer(model, src, dst, n, x, e, y, 0, 1, torch.device('cuda'), pos_weight=1 / 3)
+    loss = tr.step(None)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-6
+    for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        scale = max(float(q.grad.abs().max()), 1e-6)
+        assert float((p.grad - q.grad).abs().max()) <= 1e-5 * scale + 1e-7, k
+    for (k, b), (_, c) in zip(model.named_buffers(), ref.named_buffers()):
+        torch.testing.assert_close(b, c, rtol=1e-6, atol=1e-7, msg=k)
+    # a second step with the check-point switched off gives the same loss as with it (same parameters)
+    tr2 = train_dist.ShardedTrainer(copy.deepcopy(ref), src, dst, n, x, e, y, 0, 1, torch.device('cuda'), pos_weight=1 / 3,
+                                    checkpoint=False)
+    tr2.model.zero_grad(set_to_none=True)
+    assert abs(float(tr2.step(None)) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
