@@ -48,8 +48,8 @@ WORKLOADS = {
 }
 TRAIN_WORKLOADS = ('cfg5', 'cfg5s', 'cfg5t')
 CPU_TRAIN_SAMPLE = (10_000, 60_000)  # bounded sample for the CPU arm of the training workloads
-CPU_SAMPLE = (40_000, 240_000)      # bounded sample of the workload for the CPU arm (same H, L, generator)
-CPU_PASSES = 3                      # timed passes of the CPU arm inside the default GPU run (after one warm-up pass)
+CPU_SAMPLE = (200_000, 1_200_000)   # bounded sample of the workload for the CPU arm (same H, L, generator): ~17 GB of host RAM
+CPU_PASSES = 1                      # timed passes of the CPU arm inside the default GPU run (after one warm-up pass; ~15 s each)
 if os.environ.get('GNB_BENCH_CPU_SAMPLE'):   # tests shrink it
     CPU_SAMPLE = tuple(int(v) for v in os.environ['GNB_BENCH_CPU_SAMPLE'].split(','))
 HIDDEN_NE, HIDDEN_SCORES = 16, 64   # configs/hyperparameters.py:24-25 of the reference
@@ -251,6 +251,48 @@ def cpu_oracle_run(state_dict, H, L, steps, warmup, sample=CPU_SAMPLE, seed=1):
     return dict(n=n, m=m, times=times, out=out, inputs=(src, dst, x, e), cores=cores)
 
 
+def cross_backend_parity(device):
+    """Parity at size where the CPU oracle cannot go: the tcgen05 / split-fp16 product path against the CUDA-core
+    fp32 kernels (an independent code path: own graph walk, own arithmetic) at BASELINE config 2's FULL size."""
+    import gnnome_b200
+    n, m, H, L, _ = WORKLOADS['cfg2']
+    model = make_model(H, L, device)
+    src, dst, x, e = make_inputs(n, m, seed=0)
+    with torch.no_grad():
+        gi = gnnome_b200.GraphIndex(src, dst, n, device)
+        x_d, e_d = x.to(device), e.to(device)
+        a = model(gi, x_d, e_d)
+        gnnome_b200.set_backend('ffma')
+        try:
+            b = model(gi, x_d, e_d)
+        finally:
+            gnnome_b200.set_backend('tc2')
+        err = (torch.sigmoid(a.double()) - torch.sigmoid(b.double())).abs().max().item()
+    return {'workload': f'cfg2 full size (N={n} E={m} H={H} L={L})', 'backends': 'tc2 (tcgen05, split fp16 state) vs ffma (CUDA cores, fp32)',
+            'max_prob_diff': err}
+
+
+def cfg1_standin_parity(device):
+    """BASELINE config 1 (the E. coli example through hifiasm -> DGL -> inference.py) cannot be produced here: hifiasm,
+    Biopython and DGL are absent.  Its stand-in, as SURVEY.md section 8(c)(iv) prescribes: an E. coli-sized synthetic
+    assembly graph scored with the reference's SHIPPED weights, GPU path vs the CPU oracle."""
+    import gnnome_b200
+    from oracle import restatement as R   # checker only (cpu_baseline leg)
+    sd = torch.load(os.path.join(ROOT, 'tests', 'golden', 'weights.pt'), weights_only=True)
+    n, m = 15_000, 100_000
+    src, dst, x, e = make_inputs(n, m, seed=7)
+    model = gnnome_b200.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch')
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(device)
+    with torch.no_grad():
+        out = model((src, dst, n), x.to(device), e.to(device))
+        ref = R.model_forward(sd, src, dst, n, x, e, faithful=True)
+    err = (torch.sigmoid(out.double().cpu()) - torch.sigmoid(ref.double())).abs().max().item()
+    return {'what': f'stand-in for BASELINE config 1: E. coli-sized synthetic assembly graph (N={n} E={m}), the reference\'s '
+                    f'shipped weights/weights.pt (H=64, L=8); the real example needs hifiasm + Biopython + DGL',
+            'max_prob_err_vs_oracle': err}
+
+
 def run_reference_arm(args, wl):
     rank, _, world = dist_env()
     if rank != 0:
@@ -407,6 +449,23 @@ def run_gpu_arm(args, wl):
                'includes': 'per rank: H2D of its shard (local src/dst, x, e), graph staging, forward with halo '
                            'exchanges, D2H of its scores; max over ranks'}
 
+    # ---- N > 1: the sharded forward against the single-GPU forward of the same model on a sample graph ----------
+    parity_multi = None
+    if world > 1:
+        import torch.distributed as dist
+        from gnnome_b200 import partition
+        dog.arm('sharded-vs-single parity', 4)
+        sn, sm = 200_000, 1_200_000
+        s_src, s_dst, s_x, s_e = make_inputs(sn, sm, seed=1)
+        with torch.no_grad():
+            r2 = partition.ShardedForward(model, s_src, s_dst, sn, s_x, s_e, rank, world, device)
+            full = partition.gather_scores(r2, r2.step(), sm)
+            if rank == 0:
+                single = model((s_src, s_dst, sn), s_x.to(device), s_e.to(device))
+                parity_multi = {'sample': f'N={sn} E={sm} H={H} L={L}, same generator',
+                                'max_prob_diff': (torch.sigmoid(full.double()) - torch.sigmoid(single.double())).abs().max().item(),
+                                'max_logit_diff': (full - single).abs().max().item()}
+        del r2, full
     dog.arm('teardown', 2)
     if world > 1:
         import torch.distributed as dist
@@ -434,6 +493,11 @@ def run_gpu_arm(args, wl):
                'sample': f'N={r["n"]} E={r["m"]} H={H} L={L}, same generator, mean of {len(r["times"])} passes after one '
                          f'warm-up ({t_cpu:.1f}s each); torch {torch.__version__} CPU threads={r["cores"]}',
                'parity_max_prob_err_on_sample': perr}
+        del r, ours
+        dog.arm('parity extras', 8)
+        cpu['parity_cross_backend'] = cross_backend_parity(device)
+        cpu['cfg1_standin'] = cfg1_standin_parity(device)
+        dog.disarm()
 
     line = {
         'metric': 'edges/s', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': args.steps,
@@ -446,6 +510,8 @@ def run_gpu_arm(args, wl):
         'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
         'kernels': breakdown,
     }
+    if parity_multi is not None:
+        line['parity_vs_single_gpu'] = parity_multi
     emit(line)
 
 

@@ -70,12 +70,27 @@ class Shard:
         self.recv_counts = torch.bincount(owner, minlength=world).tolist() if self.n_halo else [0] * world
 
 
+class DistComm:
+    """The collectives the sharded path needs, over ``torch.distributed`` (NCCL on the GPUs, gloo in the CPU tests).
+    ``tests/test_gpu_partition.py`` plugs an in-process implementation in to run k shards on ONE GPU."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def all_to_all(self, out, inp, out_splits=None, in_splits=None):
+        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group)
+
+    def all_reduce_max(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
+
 class HaloPlan:
     """Who sends which owned rows to whom.  ``send_idx`` (local owned node ids, grouped by peer rank)
     is obtained by exchanging the halo lists once."""
 
-    def __init__(self, shard: Shard, device, group=None):
+    def __init__(self, shard: Shard, device, group=None, comm=None):
         self.world, self.group = shard.world, group
+        self.comm = comm if comm is not None else DistComm(group)
         self.recv_counts = list(shard.recv_counts)
         world = shard.world
         self.active = False          # does ANY rank exchange rows?  (a collective has to be entered by every rank)
@@ -85,17 +100,16 @@ class HaloPlan:
             return
         cnt_in = torch.tensor(self.recv_counts, dtype=torch.int64, device=device)
         cnt_out = torch.empty(world, dtype=torch.int64, device=device)
-        dist.all_to_all_single(cnt_out, cnt_in, group=group)
+        self.comm.all_to_all(cnt_out, cnt_in)
         self.send_counts = cnt_out.tolist()
         want = shard.halo_nodes.to(device=device, dtype=torch.int64).contiguous()
         asked = torch.empty(sum(self.send_counts), dtype=torch.int64, device=device)
-        dist.all_to_all_single(asked, want, output_split_sizes=self.send_counts,
-                               input_split_sizes=self.recv_counts, group=group)
+        self.comm.all_to_all(asked, want, self.send_counts, self.recv_counts)
         if asked.numel() and (int(asked.min()) < shard.lo or int(asked.max()) >= shard.hi):
             raise RuntimeError('halo plan: a peer asked for a node this rank does not own')
         self.send_idx = (asked - shard.lo).to(torch.int32).contiguous()
         busy = torch.tensor([int(shard.n_halo > 0 or asked.numel() > 0)], dtype=torch.int64, device=device)
-        dist.all_reduce(busy, op=dist.ReduceOp.MAX, group=group)
+        self.comm.all_reduce_max(busy)
         self.active = bool(busy.item())
         # reverse exchange: rows arrive in send_idx order; group them per owned node (stable => rank order)
         order = torch.argsort(self.send_idx.long(), stable=True)
@@ -111,15 +125,13 @@ class HaloPlan:
     def to_consumers(self, rows_out, recv):
         """owner -> consumer: ``rows_out`` [n_send][W] (send_idx order) -> ``recv`` [n_halo][W]."""
         if self.world > 1:
-            dist.all_to_all_single(recv, rows_out, output_split_sizes=self.recv_counts,
-                                   input_split_sizes=self.send_counts, group=self.group)
+            self.comm.all_to_all(recv, rows_out, self.recv_counts, self.send_counts)
         return recv
 
     def to_owners(self, rows_out, recv):
         """consumer -> owner: ``rows_out`` [n_halo][W] -> ``recv`` [n_send][W] (send_idx order)."""
         if self.world > 1:
-            dist.all_to_all_single(recv, rows_out, output_split_sizes=self.send_counts,
-                                   input_split_sizes=self.recv_counts, group=self.group)
+            self.comm.all_to_all(recv, rows_out, self.send_counts, self.recv_counts)
         return recv
 
 
@@ -232,7 +244,7 @@ class ShardedForward:
     same); only the shard is kept on the device."""
 
     def __init__(self, model, src, dst, num_nodes, x, e, rank, world, device, kernels=None, group=None,
-                 dtype=torch.float32):
+                 dtype=torch.float32, comm=None):
         self.model, self.rank, self.world, self.device, self.group = model, rank, world, device, group
         self.dtype = dtype   # fp32 on the CUDA path; the CPU emulation in the tests runs fp64
         self.k = kernels if kernels is not None else CudaKernels(device)
@@ -245,7 +257,7 @@ class ShardedForward:
         if torch.device(device).type == 'cuda':          # build the index tables on the GPU (sort / unique of E ids)
             src, dst = src.to(device), dst.to(device)
         self.shard = sh = Shard(src, dst, num_nodes, rank, world)
-        self.plan = HaloPlan(sh, device, group)
+        self.plan = HaloPlan(sh, device, group, comm)
         self.owned_edge_ids = sh.edge_ids
         self.gi = self.k.stage(sh.src_local.to(device), sh.dst_local.to(device), sh.n_local)
         self.x_own = torch.as_tensor(x)[sh.lo:sh.hi].to(device=device, dtype=dtype).contiguous()

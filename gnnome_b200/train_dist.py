@@ -238,7 +238,10 @@ class ShardedTrainer:
 
     def __init__(self, model, src, dst, num_nodes, x, e, y, rank, world, device, pos_weight=None, prims=None, group=None,
                  dtype=torch.float32, checkpoint=True):
-        self.model, self.rank, self.world, self.device, self.group = model, rank, world, torch.device(device), group
+        device = torch.device(device)
+        if device.type == 'cuda' and device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.model, self.rank, self.world, self.device, self.group = model, rank, world, device, group
         self.dtype, self.checkpoint = dtype, checkpoint
         self.p = prims if prims is not None else CudaPrims(self.device)
         self.sym = hasattr(model, 'linear1_node')

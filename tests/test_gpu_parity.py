@@ -309,3 +309,51 @@ def test_full_size_properties_cfg2(gnb):
         perm = torch.randperm(m, generator=torch.Generator().manual_seed(1))
         c = model((src[perm], dst[perm], n), xd, ed[perm.cuda()])
     assert _prob_err(a[perm.cuda()], c) <= PROB_TOL
+
+
+def test_cross_backend_at_cfg2_full_size(gnb):
+    """Parity at the measured size (the oracle cannot hold it): BASELINE config 2 in full -- 1M nodes / 6M edges, H=128,
+    L=8 -- on the tcgen05 / split-fp16 product path against the CUDA-core fp32 kernels, an independent code path (own
+    graph walk, fp32 state, FFMA products).  int32 positions x row strides, 25 k tiles per CTA and the L2-evicting
+    working set only exist at this size."""
+    n, m, H, L = 1_000_000, 6_000_000, 128, 8
+    src, dst, n, x, e = _graph(n, m, seed=0)
+    torch.manual_seed(0)
+    model = gnb.models.SymGatedGCNModel(2, 2, H, 16, L, 64, 'batch').cuda().eval()
+    with torch.no_grad():
+        gi = gnb.GraphIndex(src, dst, n)
+        xd, ed = x.cuda(), e.cuda()
+        a = model(gi, xd, ed)
+        gnb.set_backend('ffma')
+        try:
+            b = model(gi, xd, ed)
+        finally:
+            gnb.set_backend('tc2')
+    assert _prob_err(a, b) <= 2e-5
+
+
+def test_model_vs_oracle_h256_l8_at_1m2_edges(gnb):
+    """The largest oracle comparison the host can hold at the benchmark's model shape: H=256, L=8 on 200k nodes /
+    1.2M edges (~17 GB of host RAM on the reference path), probabilities within 1e-4 (measured ~3e-6)."""
+    n, m, H, L = 200_000, 1_200_000, 256, 8
+    src, dst, n, x, e = _graph(n, m, seed=1)
+    torch.manual_seed(0)
+    model = gnb.models.SymGatedGCNModel(2, 2, H, 16, L, 64, 'batch').eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        out = model.cuda()((src, dst, n), x.cuda(), e.cuda())
+        ref = R.model_forward(sd, src, dst, n, x, e, faithful=False)
+    assert _prob_err(out, ref) <= PROB_TOL
+
+
+def test_cfg1_standin_shipped_weights_ecoli_sized(gnb, shipped_weights):
+    """BASELINE config 1 stand-in (SURVEY.md section 8(c)(iv)): the real E. coli graph needs hifiasm + Biopython + DGL;
+    an E. coli-sized synthetic assembly graph (15k nodes / 100k edges) with the reference's shipped weights."""
+    src, dst, n, x, e = _graph(15_000, 100_000, seed=7)
+    model = gnb.models.SymGatedGCNModel(2, 2, 64, 16, 8, 64, 'batch')
+    model.load_state_dict(shipped_weights)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model((src, dst, n), x.cuda(), e.cuda())
+        ref = R.model_forward(shipped_weights, src, dst, n, x, e, faithful=True)
+    assert _prob_err(out, ref) <= PROB_TOL
