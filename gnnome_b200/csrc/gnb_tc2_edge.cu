@@ -247,11 +247,20 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 #pragma unroll
       for (int l = 0; l < C::HC * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + l * 128));
     };
-    int cur[3], nxt[3];
-    if (worker < num_tiles) load_idx(worker, cur);
+    // The endpoints are read kIdxAhead tiles ahead of their use: a load issued in one iteration and consumed in the
+    // next made every iteration of this loop one DRAM round trip long -- about a tile period, so the producer could not
+    // run ahead and the epilogue groups waited for their indices 12 % of the time (profiles/r02c).
+    constexpr int kIdxAhead = 3;
+    int ring[kIdxAhead][3];
+#pragma unroll
+    for (int k = 0; k < kIdxAhead; ++k)
+      if (worker + (int64_t)k * workers < num_tiles) load_idx(worker + (int64_t)k * workers, ring[k]);
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       const int s = i % C::NB;
+      int cur[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cur[k] = ring[0][k];
       prefetch_rows(cur);
       mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkEdge2, kWrProducer, kWbEmpty), s, i);
       if (elect_one()) {
@@ -268,15 +277,18 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           }
         }
       }
-      if (t + workers < num_tiles) load_idx(t + workers, nxt);   // in flight while this tile's indices are published
+#pragma unroll
+      for (int k = 0; k + 1 < kIdxAhead; ++k) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ring[k][j] = ring[k + 1][j];
+      }
+      if (t + (int64_t)kIdxAhead * workers < num_tiles) load_idx(t + (int64_t)kIdxAhead * workers, ring[kIdxAhead - 1]);
       const int grp = i % kE2Groups, slot = (i / kE2Groups) % kE2IdxSlots;
       int* ia = idx_area + (grp * kE2IdxSlots + slot) * kE2IdxInts;
       ia[lane] = cur[0];
       ia[kE2NT + lane] = cur[1];
       if (lane < 2) ia[2 * kE2NT + lane] = cur[2];
       mbar_arrive(&ifull[grp * kE2IdxSlots + slot]);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) cur[k] = nxt[k];
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issue
