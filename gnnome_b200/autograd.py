@@ -89,6 +89,37 @@ class Agg(torch.autograd.Function):
         return None, gA, gsigma, None
 
 
+class AggRaw(torch.autograd.Function):
+    """(num, den)[i] = (sum_p sigma[p] * A[nbr_p], sum_p sigma[p]) -- ``Agg`` without the division, both outputs
+    differentiable: the sharded training step adds the partial sums of several ranks before dividing."""
+
+    @staticmethod
+    def forward(ctx, gi: GraphIndex, A, sigma, mode):
+        A, sigma = _c(A), _c(sigma)
+        W = A.shape[1]
+        den = torch.empty((gi.N, W), dtype=torch.float32, device=A.device)
+        num = torch.empty_like(den)
+        _call('gnb_t_agg_fwd', A.device, gi.ref(), W, A.data_ptr(), A.stride(0), sigma.data_ptr(), mode | 2, den.data_ptr(),
+              num.data_ptr())
+        ctx.gi, ctx.W, ctx.mode = gi, W, mode
+        ctx.save_for_backward(A, sigma)
+        return num, den
+
+    @staticmethod
+    def backward(ctx, gnum, gden):
+        gi, W, mode = ctx.gi, ctx.W, ctx.mode
+        A, sigma = ctx.saved_tensors
+        gnum = torch.zeros((gi.N, W), dtype=torch.float32, device=A.device) if gnum is None else _c(gnum)
+        gden = torch.zeros((gi.N, W), dtype=torch.float32, device=A.device) if gden is None else _c(gden)
+        gsigma = torch.empty_like(sigma)
+        _call('gnb_t_agg_bwd_edge', A.device, gi.ref(), W, gnum.data_ptr(), gden.data_ptr(), None, A.data_ptr(),
+              A.stride(0), mode | 2, gsigma.data_ptr(), 0)
+        gA = torch.empty_like(A)
+        _call('gnb_t_agg_bwd_node', A.device, gi.ref(), W, gnum.data_ptr(), None, sigma.data_ptr(), mode | 2,
+              gA.data_ptr(), W)
+        return None, gA, gsigma, None
+
+
 class Gate(torch.autograd.Function):
     """e' = relu(ehat) (+ e_in), sigma = sigmoid(e')  (gated_gcn_full.py:107-111)."""
 

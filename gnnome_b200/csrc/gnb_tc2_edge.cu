@@ -74,7 +74,7 @@ struct Edge2Cfg {
   // behalf of both CTAs.
   static constexpr bool MC = NH == 2;
   using T = Tile2<H, kE2NT>;
-  static constexpr int NB = (H >= 256) ? 3 : 4;          // input stages (NB <= 4: see ifull)
+  static constexpr int NB = 4;                           // input stages (NB <= 4: see ifull)
   static_assert(NB <= 4, "index slot reuse distance");
   // the identity block [128 rows (TMEM lanes)][HC input channels] as a K-major SWIZZLE_128B A operand
   static constexpr int ID_KB_BYTES = kM * 128;
@@ -90,7 +90,8 @@ struct Edge2Cfg {
   static constexpr uint32_t D_COL0 = 2 * T::W_COLS;
   static_assert(2 * T::W_COLS + kE2Groups * kE2DCols <= 512, "tensor memory budget");
   static constexpr int NBARS = 2 * NB + kE2Groups * (kE2IdxSlots + 4);
-  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + ID_BYTES + (size_t)kE2Groups * OBUF_BYTES + 1024 +
+  // no alignment slack: the dynamic shared memory window starts 1024-byte aligned (the kernel traps if it does not)
+  static constexpr size_t SMEM = (size_t)NB * T::BUF_BYTES + ID_BYTES + (size_t)kE2Groups * OBUF_BYTES +
                                  (size_t)kE2Groups * kE2IdxSlots * kE2IdxInts * 4 + NBARS * 8 + 16;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -164,9 +165,8 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
   using C = Edge2Cfg<H>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment by pointer arithmetic on the shared array (an integer round-trip would demote every later
-  // access through these pointers to generic loads)
-  uint8_t* bufs = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // [NB] input stages
+  if (smem_u32(smem_raw) & 1023u) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment; the budget has no slack for it
+  uint8_t* bufs = smem_raw;                                                        // [NB] input stages
   uint8_t* ident = bufs + (size_t)C::NB * T::BUF_BYTES;
   uint8_t* obufs = ident + C::ID_BYTES;                                            // [G] output buffers
   int* idx_area = reinterpret_cast<int*>(obufs + (size_t)kE2Groups * C::OBUF_BYTES);   // [G][2] index slots

@@ -10,6 +10,8 @@
 //   seg_sum       out_i = sum of X_p over the in- / out-edges of i        adjoint of the gathers above
 //   agg_fwd       out_i = sum sigma_p * A[nbr_p] / (sum sigma_p + 1e-6)   update_all(u_mul_e, sum) / (copy_e, sum), :112-114, :125-127
 //   agg_bwd_edge / agg_bwd_node                                            its adjoints w.r.t. sigma and A
+//                 (mode | 2: the UN-NORMALISED sums (num, den) and their adjoints -- the sharded training step adds the
+//                 partial sums of several ranks before the division)
 //   gate_fwd/bwd  e' = relu(ehat) (+ e), sigma = sigmoid(e')             :107-111
 //   col_stats, affine2                                                     BatchNorm1d batch statistics / normalise / backward, :106,:132
 #include "gnb_common.cuh"
@@ -71,6 +73,8 @@ __global__ void seg_sum_kernel(gnb_graph_t g, int H, const float* __restrict__ X
 __global__ void agg_fwd_kernel(gnb_graph_t g, int H, const float* __restrict__ A, int64_t ldA,
                                const float* __restrict__ sigma, int mode, float* __restrict__ den,
                                float* __restrict__ out) {
+  const bool raw = mode & 2;
+  mode &= 1;
   const int h4 = H / 4;
   const int64_t total = g.num_nodes * h4;
   for (int64_t k = (int64_t)blockIdx.x * kT + threadIdx.x; k < total; k += (int64_t)gridDim.x * kT) {
@@ -91,15 +95,19 @@ __global__ void agg_fwd_kernel(gnb_graph_t g, int H, const float* __restrict__ A
       }
     }
     st4(den + i * H + c, dn);
-    st4(out + i * H + c, make_float4(num.x / (dn.x + kGateEps), num.y / (dn.y + kGateEps), num.z / (dn.z + kGateEps),
-                                     num.w / (dn.w + kGateEps)));
+    if (raw) st4(out + i * H + c, num);
+    else st4(out + i * H + c, make_float4(num.x / (dn.x + kGateEps), num.y / (dn.y + kGateEps), num.z / (dn.z + kGateEps),
+                                          num.w / (dn.w + kGateEps)));
   }
 }
 
 // gsigma[p] (+)= gnum[i_p] * A[nbr_p] + gden[i_p] with gnum = gout / (den + eps), gden = -gout * out / (den + eps)
+// (mode | 2: gout IS gnum and out IS gden, den unused)
 __global__ void agg_bwd_edge_kernel(gnb_graph_t g, int H, const float* __restrict__ gout, const float* __restrict__ out,
                                     const float* __restrict__ den, const float* __restrict__ A, int64_t ldA, int mode,
                                     float* __restrict__ gsigma, int accumulate) {
+  const bool raw = mode & 2;
+  mode &= 1;
   const int h4 = H / 4;
   const int64_t total = g.num_edges * h4;
   for (int64_t k = (int64_t)blockIdx.x * kT + threadIdx.x; k < total; k += (int64_t)gridDim.x * kT) {
@@ -107,13 +115,18 @@ __global__ void agg_bwd_edge_kernel(gnb_graph_t g, int H, const float* __restric
     const int c = (int)(k - p * h4) * 4;
     const int64_t i = mode == 0 ? g.in_dst[p] : g.in_src[p];
     const int64_t nb = mode == 0 ? g.in_src[p] : g.in_dst[p];
-    const float4 go = ld4(gout + i * H + c), o = ld4(out + i * H + c), d = ld4(den + i * H + c);
+    const float4 go = ld4(gout + i * H + c), o = ld4(out + i * H + c);
     const float4 a = ld4(A + nb * ldA + c);
     float4 r;
-    r.x = go.x / (d.x + kGateEps) * (a.x - o.x);
-    r.y = go.y / (d.y + kGateEps) * (a.y - o.y);
-    r.z = go.z / (d.z + kGateEps) * (a.z - o.z);
-    r.w = go.w / (d.w + kGateEps) * (a.w - o.w);
+    if (raw) {
+      r = fma4(go, a, o);
+    } else {
+      const float4 d = ld4(den + i * H + c);
+      r.x = go.x / (d.x + kGateEps) * (a.x - o.x);
+      r.y = go.y / (d.y + kGateEps) * (a.y - o.y);
+      r.z = go.z / (d.z + kGateEps) * (a.z - o.z);
+      r.w = go.w / (d.w + kGateEps) * (a.w - o.w);
+    }
     if (accumulate) r = add4(r, ld4(gsigma + p * H + c));
     st4(gsigma + p * H + c, r);
   }
@@ -122,6 +135,8 @@ __global__ void agg_bwd_edge_kernel(gnb_graph_t g, int H, const float* __restric
 // gA[n] = sum over the edges whose NEIGHBOUR end is n of gnum[i_p] * sigma[p]   (walks the other CSR view)
 __global__ void agg_bwd_node_kernel(gnb_graph_t g, int H, const float* __restrict__ gout, const float* __restrict__ den,
                                     const float* __restrict__ sigma, int mode, float* __restrict__ gA, int64_t ldg) {
+  const bool raw = mode & 2;   // gout is gnum: no division by (den + eps)
+  mode &= 1;
   const int h4 = H / 4;
   const int64_t total = g.num_nodes * h4;
   for (int64_t k = (int64_t)blockIdx.x * kT + threadIdx.x; k < total; k += (int64_t)gridDim.x * kT) {
@@ -131,7 +146,9 @@ __global__ void agg_bwd_node_kernel(gnb_graph_t g, int H, const float* __restric
     if (mode == 0) {   // forward aggregated over in-edges with neighbour = src: n is the SOURCE of these edges
       for (int q = g.out_ptr[n], qe = g.out_ptr[n + 1]; q < qe; ++q) {
         const int64_t p = g.out_pos[q], i = g.out_dst[q];
-        const float4 go = ld4(gout + i * H + c), d = ld4(den + i * H + c), s = ld4(sigma + p * H + c);
+        const float4 go = ld4(gout + i * H + c), s = ld4(sigma + p * H + c);
+        if (raw) { acc = fma4(go, s, acc); continue; }
+        const float4 d = ld4(den + i * H + c);
         acc.x = fmaf(go.x / (d.x + kGateEps), s.x, acc.x);
         acc.y = fmaf(go.y / (d.y + kGateEps), s.y, acc.y);
         acc.z = fmaf(go.z / (d.z + kGateEps), s.z, acc.z);
@@ -140,7 +157,9 @@ __global__ void agg_bwd_node_kernel(gnb_graph_t g, int H, const float* __restric
     } else {           // forward aggregated over out-edges with neighbour = dst: n is the DESTINATION
       for (int p = g.in_ptr[n], pe = g.in_ptr[n + 1]; p < pe; ++p) {
         const int64_t i = g.in_src[p];
-        const float4 go = ld4(gout + i * H + c), d = ld4(den + i * H + c), s = ld4(sigma + (int64_t)p * H + c);
+        const float4 go = ld4(gout + i * H + c), s = ld4(sigma + (int64_t)p * H + c);
+        if (raw) { acc = fma4(go, s, acc); continue; }
+        const float4 d = ld4(den + i * H + c);
         acc.x = fmaf(go.x / (d.x + kGateEps), s.x, acc.x);
         acc.y = fmaf(go.y / (d.y + kGateEps), s.y, acc.y);
         acc.z = fmaf(go.z / (d.z + kGateEps), s.z, acc.z);
@@ -349,7 +368,7 @@ extern "C" int gnb_t_agg_fwd(const gnb_graph_t* g, int H, const float* A, int64_
   int rc = check_train_graph(g, H);
   if (rc) return rc;
   if (g->num_nodes == 0) return 0;
-  GNB_REQUIRE(A && den && out && (sigma || g->num_edges == 0) && ldA % 4 == 0 && (mode == 0 || mode == 1),
+  GNB_REQUIRE(A && den && out && (sigma || g->num_edges == 0) && ldA % 4 == 0 && mode >= 0 && mode <= 3,
               "gnb_t_agg_fwd: bad arguments");
   agg_fwd_kernel<<<blocks_for(g->num_nodes * (H / 4)), kT, 0, (cudaStream_t)stream>>>(*g, H, A, ldA, sigma, mode, den, out);
   return check_launch("gnb_t_agg_fwd");
@@ -360,7 +379,8 @@ extern "C" int gnb_t_agg_bwd_edge(const gnb_graph_t* g, int H, const float* gout
   int rc = check_train_graph(g, H);
   if (rc) return rc;
   if (g->num_edges == 0) return 0;
-  GNB_REQUIRE(gout && out && den && A && gsigma && ldA % 4 == 0 && (mode == 0 || mode == 1), "gnb_t_agg_bwd_edge: bad arguments");
+  GNB_REQUIRE(gout && out && (den || (mode & 2)) && A && gsigma && ldA % 4 == 0 && mode >= 0 && mode <= 3,
+              "gnb_t_agg_bwd_edge: bad arguments");
   agg_bwd_edge_kernel<<<blocks_for(g->num_edges * (H / 4)), kT, 0, (cudaStream_t)stream>>>(*g, H, gout, out, den, A, ldA,
                                                                                          mode, gsigma, accumulate);
   return check_launch("gnb_t_agg_bwd_edge");
@@ -371,7 +391,7 @@ extern "C" int gnb_t_agg_bwd_node(const gnb_graph_t* g, int H, const float* gout
   int rc = check_train_graph(g, H);
   if (rc) return rc;
   if (g->num_nodes == 0) return 0;
-  GNB_REQUIRE(gout && den && gA && (sigma || g->num_edges == 0) && ldg % 4 == 0 && (mode == 0 || mode == 1),
+  GNB_REQUIRE(gout && (den || (mode & 2)) && gA && (sigma || g->num_edges == 0) && ldg % 4 == 0 && mode >= 0 && mode <= 3,
               "gnb_t_agg_bwd_node: bad arguments");
   agg_bwd_node_kernel<<<blocks_for(g->num_nodes * (H / 4)), kT, 0, (cudaStream_t)stream>>>(*g, H, gout, den, sigma, mode, gA, ldg);
   return check_launch("gnb_t_agg_bwd_node");

@@ -163,26 +163,6 @@ class _LayerCheckpoint(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # the CUDA primitives
 # ------------------------------------------------------------------------------------------------
-class SegSumOut(torch.autograd.Function):
-    """out[i] = sum of the edge rows X[p] over the OUT-edges of node i (fixed order); adjoint: gX[p] = gout[src_p]."""
-
-    @staticmethod
-    def forward(ctx, gi, X):
-        from . import autograd as A
-        X = A._c(X)
-        W = X.shape[1]
-        out = torch.empty((gi.N, W), dtype=torch.float32, device=X.device)
-        A._call('gnb_t_seg_sum', X.device, gi.ref(), W, X.data_ptr(), 1, out.data_ptr(), W)
-        ctx.gi = gi
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        from . import ops
-        gi = ctx.gi
-        return None, ops.gather_rows(g.contiguous(), gi.in_src[:gi.E])
-
-
 class CudaPrims:
     """The product path: ``gnnome_b200.autograd``'s functions (hand-written forward / adjoint kernels, C ABI)."""
 
@@ -197,17 +177,14 @@ class CudaPrims:
     def position_eids(self, gi):
         return gi.in_eid[:gi.E].long()
 
-    def dst_positions(self, gi):
-        return gi.in_dst[:gi.E].long()
-
     def gather_add3(self, gi, A_, B_, C_):
         return self.A.GatherAdd3.apply(gi, A_, B_, C_)
 
     def agg_in(self, gi, A_, sigma):
         return self.A.Agg.apply(gi, A_, sigma, 0)
 
-    def seg_sum_out(self, gi, X):
-        return SegSumOut.apply(gi, X)
+    def agg_out_raw(self, gi, A_, sigma):
+        return self.A.AggRaw.apply(gi, A_, sigma, 1)
 
     def gate(self, ehat, e_in):
         return self.A.Gate.apply(ehat, e_in)
@@ -259,7 +236,6 @@ class ShardedTrainer:
         self.gi = self.p.stage(sh.src_local.to(self.device), sh.dst_local.to(self.device), sh.n_local)
         order = self.p.position_eids(self.gi)                          # local edge id at every dst-sorted position
         self.order = order
-        self.dst_pos = self.p.dst_positions(self.gi)
         ids = sh.edge_ids
         pick = lambda t: torch.as_tensor(t)[ids.to(torch.as_tensor(t).device)].to(device=self.device, dtype=dtype)  # noqa: E731
         self.x_own = torch.as_tensor(x)[sh.lo:sh.hi].to(device=self.device, dtype=dtype).contiguous()
@@ -301,8 +277,7 @@ class ShardedTrainer:
         e_new, sigma = p.gate(ehat, e if conv.residual else None)                              # :107-111
         u = A1h + p.agg_in(gi, A2h, sigma)[:n_own]                                             # :112-114
         if conv._symmetric:                                                                    # :93, :125-127
-            msg = sigma * conv.A_3(h_own).index_select(0, self.dst_pos)
-            nd = torch.cat((p.seg_sum_out(gi, msg), p.seg_sum_out(gi, sigma)), 1)              # [n_local][2H], local edges
+            nd = torch.cat(p.agg_out_raw(gi, conv.A_3(h_loc), sigma), 1)                       # [n_local][2H], local edges
             tot = nd[:n_own]
             if self.plan.active:
                 tot = tot + HaloScatterAdd.apply(self.ex, nd[n_own:])                          # partial sums of remote sources

@@ -247,7 +247,10 @@ int gnb_t_gather_add3(const gnb_graph_t* g, int H, const float* A, int64_t ldA, 
 /* out[i] = sum of X[p] over the in-edges (mode 0) / out-edges (mode 1) of node i: adjoint of the gathers */
 int gnb_t_seg_sum(const gnb_graph_t* g, int H, const float* X, int mode, float* out, int64_t ldo, void* stream);
 /* out[i] = sum sigma[p] * A[nbr_p] / (den[i] + 1e-6), den[i] = sum sigma[p]; mode 0: in-edges, nbr = src
- * (gated_gcn_full.py:112-114); mode 1: out-edges, nbr = dst (:125-127) */
+ * (gated_gcn_full.py:112-114); mode 1: out-edges, nbr = dst (:125-127).  mode | 2 ("raw"): out[i] = the UN-NORMALISED
+ * sum (the sharded training step adds the partial sums of several ranks before the division); in the two adjoints
+ * below raw mode takes gout = d/d num, out = d/d den (per node) and ignores den (may be NULL):
+ *   gsigma[p] (+)= gnum[i_p] * A[nbr_p] + gden[i_p],   gA[n] = sum gnum[i_p] * sigma[p]. */
 int gnb_t_agg_fwd(const gnb_graph_t* g, int H, const float* A, int64_t ldA, const float* sigma, int mode,
                   float* den, float* out, void* stream);
 /* gsigma[p] (+)= gout[i_p] / (den[i_p] + 1e-6) * (A[nbr_p] - out[i_p]) */

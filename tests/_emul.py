@@ -140,9 +140,6 @@ class TorchPrims:
     def position_eids(self, gi):
         return gi.in_eid
 
-    def dst_positions(self, gi):
-        return gi.dst
-
     def gather_add3(self, gi, A_, B_, C_):
         return A_.index_select(0, gi.src) + B_.index_select(0, gi.dst) + C_
 
@@ -152,8 +149,9 @@ class TorchPrims:
         den = z().index_add(0, gi.dst, sigma)
         return num / (den + EPS)
 
-    def seg_sum_out(self, gi, X):
-        return torch.zeros((gi.N, X.shape[1]), dtype=X.dtype).index_add(0, gi.src, X)
+    def agg_out_raw(self, gi, A_, sigma):
+        z = lambda: torch.zeros((gi.N, sigma.shape[1]), dtype=sigma.dtype)  # noqa: E731
+        return z().index_add(0, gi.src, sigma * A_.index_select(0, gi.dst)), z().index_add(0, gi.src, sigma)
 
     def gate(self, ehat, e_in):
         e_new = torch.relu(ehat) if e_in is None else torch.relu(ehat) + e_in

@@ -274,3 +274,26 @@ def test_sharded_trainer_world1_matches_the_model_training_path(gnb, kind):
                                     checkpoint=False)
     tr2.model.zero_grad(set_to_none=True)
     assert abs(float(tr2.step(None)) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_raw_aggregation_forward_and_adjoint(gnb, mode):
+    """AggRaw: the un-normalised (num, den) sums the sharded training step exchanges, against torch autograd in fp64."""
+    from gnnome_b200 import autograd as ag
+    n, m, W = 60, 500, 32
+    src, dst = _rand_graph(n, m, 5 + mode)
+    gi = gnb.GraphIndex(src, dst, n)
+    ps, pd = gi.in_src[:m].long(), gi.in_dst[:m].long()
+    torch.manual_seed(mode)
+    A = torch.randn(n, W, device='cuda', dtype=torch.float64, requires_grad=True)
+    S = torch.rand(m, W, device='cuda', dtype=torch.float64, requires_grad=True)
+    A32, S32 = (t.detach().float().requires_grad_(True) for t in (A, S))
+    node, nbr = (pd, ps) if mode == 0 else (ps, pd)
+    num_r, den_r = _seg(A[nbr] * S, node, n), _seg(S, node, n)
+    num_o, den_o = ag.AggRaw.apply(gi, A32, S32, mode)
+    assert (num_o.double() - num_r).abs().max().item() < 2e-5 and (den_o.double() - den_r).abs().max().item() < 2e-5
+    w = torch.linspace(0.5, 1.5, W, device='cuda', dtype=torch.float64)
+    ((num_r * w).sum() + (den_r * den_r).sum() * 0.1).backward()
+    ((num_o * w.float()).sum() + (den_o * den_o).sum() * 0.1).backward()
+    for a, b in ((A32, A), (S32, S)):
+        assert (a.grad.double() - b.grad).abs().max().item() < 1e-4 * max(1.0, b.grad.abs().max().item())
