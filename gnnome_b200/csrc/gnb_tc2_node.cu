@@ -336,7 +336,7 @@ struct Nu3Cfg {
   static constexpr int CW = H / 32;                             // consumer warps
   static constexpr int THREADS = H + 32;
   static constexpr size_t RING_BYTES = (size_t)NBATCH * kNu3Batch * ROW_BYTES;
-  static constexpr size_t SMEM = RING_BYTES + (size_t)NBATCH * kNu3Batch * 4 + 2 * NBATCH * 8 + 16 * 4;
+  static constexpr size_t SMEM = RING_BYTES + (size_t)NBATCH * kNu3Batch * 4 + 3 * NBATCH * 8 + 16 * 4;
 };
 
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -347,7 +347,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
 }
 
 template <int H>
-__global__ void __launch_bounds__(Nu3Cfg<H>::THREADS)
+__global__ void __launch_bounds__(Nu3Cfg<H>::THREADS, 3)
 node_update3_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ e16,
                     const float* __restrict__ F, const float* __restrict__ carry, const float* __restrict__ h_in,
                     const float* __restrict__ scale_h, const float* __restrict__ shift_h, float* __restrict__ h_out,
@@ -360,7 +360,8 @@ node_update3_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
   int* dst_s = reinterpret_cast<int*>(ring + C::RING_BYTES);               // [NBATCH][8]
   uint64_t* full = reinterpret_cast<uint64_t*>(dst_s + C::NBATCH * kNu3Batch);
   uint64_t* empty = full + C::NBATCH;
-  int64_t* range = reinterpret_cast<int64_t*>(empty + C::NBATCH);          // [2] node range of this CTA
+  uint64_t* ifull = empty + C::NBATCH;                                     // destinations of the batch published
+  int64_t* range = reinterpret_cast<int64_t*>(ifull + C::NBATCH);          // [2] node range of this CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool residual = flags & GNB_F_RESIDUAL;
   const int a1_off = 4 * H;                                                 // symmetric layout (this kernel runs Sym / partial only)
@@ -382,6 +383,7 @@ node_update3_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
     for (int b = 0; b < C::NBATCH; ++b) {
       mbar_init(&full[b], 1);
       mbar_init(&empty[b], C::CW);
+      mbar_init(&ifull[b], 1);
     }
     fence_barrier_init();
   }
@@ -392,25 +394,46 @@ node_update3_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
 
   if (warp == C::CW) {
     // ---------------------------------------------------------------- producer
-    int64_t b = 0;
-    for (int64_t q = q0; q < q1; q += kNu3Batch, ++b) {
-      const int sb = (int)(b % C::NBATCH);
-      mbar_wait(&empty[sb], (uint32_t)(((b / C::NBATCH) & 1) ^ 1), 32, watch, watch_tag(kWkNode3, kWrProducer, kWbEmpty), sb, b);
-      const int cnt = (int)((q1 - q < kNu3Batch) ? (q1 - q) : kNu3Batch);
-      int64_t pos = 0;
-      if (lane < cnt) {
-        pos = g.out_pos[q + lane];
-        const int d = g.out_dst[q + lane];
-        dst_s[sb * kNu3Batch + lane] = d;
-        const char* a = reinterpret_cast<const char*>(P + (int64_t)d * ldP + 3 * H);
-#pragma unroll
-        for (int l = 0; l < H * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
+    // (out_pos, out_dst) are read 32 edges -- four batches -- at a time, one group AHEAD of the copies that use them:
+    // a load consumed in the iteration that issued it made every batch one DRAM round trip long, i.e. the producer
+    // could never run ahead of the consumers.
+    int64_t pos_n = 0;
+    int d_n = 0;
+    if (q0 + lane < q1) {
+      pos_n = g.out_pos[q0 + lane];
+      d_n = g.out_dst[q0 + lane];
+    }
+    for (int64_t qg = q0; qg < q1; qg += 32) {
+      const int64_t pos = pos_n;
+      const int d = d_n;
+      if (qg + 32 + lane < q1) {
+        pos_n = g.out_pos[qg + 32 + lane];
+        d_n = g.out_dst[qg + 32 + lane];
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_expect_tx(&full[sb], (uint32_t)(cnt * C::ROW_BYTES));
-      __syncwarp();
-      if (lane < cnt)
-        bulk_copy_g2s(ring + (size_t)(sb * kNu3Batch + lane) * C::ROW_BYTES, e16 + pos * 2 * H, C::ROW_BYTES, &full[sb]);
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int64_t q = qg + j * kNu3Batch;
+        if (q >= q1) break;
+        const int64_t b = (q - q0) / kNu3Batch;
+        const int sb = (int)(b % C::NBATCH);
+        mbar_wait(&empty[sb], (uint32_t)(((b / C::NBATCH) & 1) ^ 1), 32, watch, watch_tag(kWkNode3, kWrProducer, kWbEmpty), sb, b);
+        const int cnt = (int)((q1 - q < kNu3Batch) ? (q1 - q) : kNu3Batch);
+        const bool mine = (lane >> 3) == j && (lane & 7) < cnt;
+        if (mine) {
+          dst_s[sb * kNu3Batch + (lane & 7)] = d;
+          const char* a = reinterpret_cast<const char*>(P + (int64_t)d * ldP + 3 * H);
+#pragma unroll
+          for (int l = 0; l < H * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ifull[sb]);          // the consumers start the batch's A3h gathers one batch ahead of its rows
+          mbar_arrive_expect_tx(&full[sb], (uint32_t)(cnt * C::ROW_BYTES));
+        }
+        __syncwarp();
+        if (mine)
+          bulk_copy_g2s(ring + (size_t)(sb * kNu3Batch + (lane & 7)) * C::ROW_BYTES, e16 + pos * 2 * H, C::ROW_BYTES, &full[sb]);
+      }
     }
     return;
   }
@@ -421,7 +444,18 @@ node_update3_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
   const float* Pa3 = P + 3 * H + t;
   int64_t q = q0;
   int64_t waited = -1;                       // batch whose rows have landed
-  float a3[kNu3Batch];
+  const int64_t nbatches = (q1 - q0 + kNu3Batch - 1) / kNu3Batch;
+  float a3[kNu3Batch], a3n[kNu3Batch];     // A3h[dst] of the current batch and of the next one (in flight)
+  auto gather_a3 = [&](int64_t b, float (&dstv)[kNu3Batch]) {
+    const int sb = (int)(b % C::NBATCH);
+    mbar_wait(&ifull[sb], (uint32_t)((b / C::NBATCH) & 1), 20, watch, watch_tag(kWkNode3, kWrEpilogue, kWbDFull), sb, b);
+    const int4 d0 = *reinterpret_cast<const int4*>(dst_s + sb * kNu3Batch), d1 = *reinterpret_cast<const int4*>(dst_s + sb * kNu3Batch + 4);
+    const int dd[kNu3Batch] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const int cnt = (int)((q1 - q0 - b * kNu3Batch < kNu3Batch) ? (q1 - q0 - b * kNu3Batch) : kNu3Batch);
+#pragma unroll
+    for (int r = 0; r < kNu3Batch; ++r) dstv[r] = (r < cnt) ? __ldg(Pa3 + (int64_t)dd[r] * ldP) : 0.f;
+  };
+  if (nbatches > 0) gather_a3(0, a3n);
   // node-only operands, loaded one node ahead
   int pa = 0, pb = 0;
   float a1 = 0.f, hin = 0.f, f0 = 0.f;
@@ -450,14 +484,12 @@ node_update3_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
     while (q < qb) {
       const int64_t k = q - q0, b = k / kNu3Batch;
       const int sb = (int)(b % C::NBATCH);
-      if (b != waited) {                     // first touch of this batch: wait for its rows, start its A3h gathers
+      if (b != waited) {                     // first touch of this batch: its gathers were started a batch ago
+#pragma unroll
+        for (int r = 0; r < kNu3Batch; ++r) a3[r] = a3n[r];
+        if (b + 1 < nbatches) gather_a3(b + 1, a3n);
         mbar_wait(&full[sb], (uint32_t)((b / C::NBATCH) & 1), 20, watch, watch_tag(kWkNode3, kWrEpilogue, kWbFull), sb, b);
         waited = b;
-        const int4 d0 = *reinterpret_cast<const int4*>(dst_s + sb * kNu3Batch), d1 = *reinterpret_cast<const int4*>(dst_s + sb * kNu3Batch + 4);
-        const int dd[kNu3Batch] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const int cnt = (int)((q1 - q0 - b * kNu3Batch < kNu3Batch) ? (q1 - q0 - b * kNu3Batch) : kNu3Batch);
-#pragma unroll
-        for (int r = 0; r < kNu3Batch; ++r) a3[r] = (r < cnt) ? __ldg(Pa3 + (int64_t)dd[r] * ldP) : 0.f;
       }
       const int r0 = (int)(k % kNu3Batch);
       const int r1 = (int)(((qb - q0) < (b + 1) * kNu3Batch) ? (qb - q0 - b * kNu3Batch) : kNu3Batch);   // end row (exclusive) of this node in the batch

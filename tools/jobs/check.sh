@@ -6,7 +6,7 @@
 #   bench[:WL]       bench.py --workload WL (default cfg3) -> gpurun_out/bench_WL.json + a one-line summary
 #   ref              bench.py --impl reference
 #   stress[:WL:N:P]  P fresh processes x N forwards of workload WL (tools/stress.py), default cfg3:100:3
-#   dist:N           tools/dist_check.py + bench.py under torchrun on N GPUs
+#   dist:N[:WL]      tools/dist_check.py (inference + training equivalence) + bench.py --workload WL (default cfg3) under torchrun on N GPUs
 #   sanitize[:TOOL]  compute-sanitizer --tool TOOL (default synccheck) over the small liveness / parity tests
 cd "${GRAFT_REPO_ROOT:-.}" || exit 1
 mkdir -p gpurun_out
@@ -41,7 +41,8 @@ for st in "${steps[@]}"; do
            for i in $(seq 1 "$p"); do timeout 900 python tools/stress.py "$wl" "$n" > /dev/null 2> "gpurun_out/stress_$i.err"; echo "stress $wl x$n process $i rc=$? $(grep -c ' ok ' gpurun_out/stress_$i.err) forwards ok; $(tail -1 gpurun_out/stress_$i.err)"; done ;;
     dist)  n=${a1:-2}
            timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py > "gpurun_out/dist_check_x$n.log" 2>&1; echo "dist_check x$n rc=$?"; tail -4 "gpurun_out/dist_check_x$n.log"
-           timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus "$n" --steps 5 --warmup 3 > "gpurun_out/bench_cfg3_x$n.json" 2> "gpurun_out/bench_cfg3_x$n.err"; echo "bench x$n rc=$?"; summ "gpurun_out/bench_cfg3_x$n.json" ;;
+           wl=${a2:-cfg3}
+           timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus "$n" --workload "$wl" --steps 5 --warmup 3 > "gpurun_out/bench_${wl}_x$n.json" 2> "gpurun_out/bench_${wl}_x$n.err"; echo "bench $wl x$n rc=$?"; summ "gpurun_out/bench_${wl}_x$n.json" ;;
     sanitize) tool=${a1:-synccheck}
            timeout 1500 compute-sanitizer --tool "$tool" python -m pytest tests/test_gpu_liveness.py -q -x -k "stalled and 3000" > "gpurun_out/sanitize_$tool.log" 2>&1; echo "sanitize $tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed" "gpurun_out/sanitize_$tool.log" | tail -3 ;;
     *) echo "unknown step $st" ;;
