@@ -1,7 +1,5 @@
 // CUDA-core kernels of the split16 path (gnb_tma.cuh): the input encoders and the reverse aggregation + node update.
 // They stream: every byte is touched once, so the work is organised for coalescing and loads in flight, not flops.
-#include <stdlib.h>
-
 #include "gnb_tma.cuh"
 
 namespace gnb {
@@ -309,248 +307,6 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Reverse aggregation + node update, streaming edition (gated_gcn_full.py:117-137).
-//
-// node_update2_kernel above gives a group of H / 8 threads one node at a time: out_ptr -> (out_pos, out_dst) -> the
-// e' rows are DEPENDENT loads, a node has ~6 out-edges, and while a group waits for its indices it has no row in
-// flight -- 7 warps stalled on a load per issue slot, ~60 % of the HBM peak (profiles/r02b).  Here the rows are
-// brought in by a PRODUCER that runs ahead of the arithmetic on its own:
-//   * a CTA owns a contiguous range of nodes, i.e. a contiguous range [q0, q1) of the src-sorted edge list;
-//   * the producer warp walks that list eight edges at a time: it reads (out_pos, out_dst) with coalesced loads,
-//     publishes the destinations, pulls the A3h rows of the batch into L2 and issues one bulk async copy
-//     (cp.async.bulk, 4H bytes: hi | lo images of the row) per edge into a ring of row slots in shared memory,
-//     completion counted on the batch's mbarrier -- no registers in flight, the ring depth is the prefetch depth;
-//   * the H consumer threads own ONE channel each and walk the edges in order (like the edge pass: per-source sums are
-//     register accumulators closed at CTA-uniform node boundaries, fixed summation order), reading the e' row from
-//     the ring (two 2-byte shared loads per edge) and A3h[dst] from L2 (coalesced), eight loads in flight per batch;
-//     a node is finished -- F / carry resolution, bn_h, relu, residual, fp32 + split16 output -- when its last
-//     edge has been consumed; the rows a node needs only once (A1h, h, F) are loaded one node ahead.
-// ------------------------------------------------------------------------------------------------
-constexpr int kNu3Batch = 8;       // rows per ring batch (one mbarrier pair)
-
-template <int H>
-struct Nu3Cfg {
-  static constexpr int ROW_BYTES = 4 * H;                       // hi | lo
-  static constexpr int NBATCH = 6;
-  static constexpr int CW = H / 32;                             // consumer warps
-  static constexpr int THREADS = H + 32;
-  static constexpr size_t RING_BYTES = (size_t)NBATCH * kNu3Batch * ROW_BYTES;
-  static constexpr size_t SMEM = RING_BYTES + (size_t)NBATCH * kNu3Batch * 4 + 3 * NBATCH * 8 + 16 * 4;
-};
-
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <int H>
-__global__ void __launch_bounds__(Nu3Cfg<H>::THREADS, 3)
-node_update3_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ e16,
-                    const float* __restrict__ F, const float* __restrict__ carry, const float* __restrict__ h_in,
-                    const float* __restrict__ scale_h, const float* __restrict__ shift_h, float* __restrict__ h_out,
-                    __half* __restrict__ h16_out, int flags, int chunk, int64_t node_begin, int64_t node_end,
-                    const int32_t* __restrict__ xp_ptr, const int32_t* __restrict__ xp_row,
-                    const float* __restrict__ xp_buf, float* __restrict__ partial_out, const Watch watch) {
-  using C = Nu3Cfg<H>;
-  extern __shared__ __align__(128) uint8_t smem_nu3[];
-  uint8_t* ring = smem_nu3;
-  int* dst_s = reinterpret_cast<int*>(ring + C::RING_BYTES);               // [NBATCH][8]
-  uint64_t* full = reinterpret_cast<uint64_t*>(dst_s + C::NBATCH * kNu3Batch);
-  uint64_t* empty = full + C::NBATCH;
-  uint64_t* ifull = empty + C::NBATCH;                                     // destinations of the batch published
-  int64_t* range = reinterpret_cast<int64_t*>(ifull + C::NBATCH);          // [2] node range of this CTA
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool residual = flags & GNB_F_RESIDUAL;
-  const int a1_off = 4 * H;                                                 // symmetric layout (this kernel runs Sym / partial only)
-
-  if (threadIdx.x == 0) {
-    // node range: equal shares of the weight  w(i) = out-edges before i + 4 * nodes before i  (monotone in i)
-    const int64_t base = g.out_ptr[node_begin];
-    const int64_t total = (g.out_ptr[node_end] - base) + 4 * (node_end - node_begin);
-    for (int k = 0; k < 2; ++k) {
-      const int64_t target = total / gridDim.x * (blockIdx.x + k) + (total % gridDim.x) * (blockIdx.x + k) / gridDim.x;
-      int64_t lo = node_begin, hi = node_end;                                // first i with w(i) >= target
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if ((g.out_ptr[mid] - base) + 4 * (mid - node_begin) >= target) hi = mid;
-        else lo = mid + 1;
-      }
-      range[k] = (blockIdx.x + k == gridDim.x) ? node_end : lo;
-    }
-    for (int b = 0; b < C::NBATCH; ++b) {
-      mbar_init(&full[b], 1);
-      mbar_init(&empty[b], C::CW);
-      mbar_init(&ifull[b], 1);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-  const int64_t n0 = range[0], n1 = range[1];
-  if (n0 >= n1) return;
-  const int64_t q0 = g.out_ptr[n0], q1 = g.out_ptr[n1];
-
-  if (warp == C::CW) {
-    // ---------------------------------------------------------------- producer
-    // (out_pos, out_dst) are read 32 edges -- four batches -- at a time, one group AHEAD of the copies that use them:
-    // a load consumed in the iteration that issued it made every batch one DRAM round trip long, i.e. the producer
-    // could never run ahead of the consumers.
-    int64_t pos_n = 0;
-    int d_n = 0;
-    if (q0 + lane < q1) {
-      pos_n = g.out_pos[q0 + lane];
-      d_n = g.out_dst[q0 + lane];
-    }
-    for (int64_t qg = q0; qg < q1; qg += 32) {
-      const int64_t pos = pos_n;
-      const int d = d_n;
-      if (qg + 32 + lane < q1) {
-        pos_n = g.out_pos[qg + 32 + lane];
-        d_n = g.out_dst[qg + 32 + lane];
-      }
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int64_t q = qg + j * kNu3Batch;
-        if (q >= q1) break;
-        const int64_t b = (q - q0) / kNu3Batch;
-        const int sb = (int)(b % C::NBATCH);
-        mbar_wait(&empty[sb], (uint32_t)(((b / C::NBATCH) & 1) ^ 1), 32, watch, watch_tag(kWkNode3, kWrProducer, kWbEmpty), sb, b);
-        const int cnt = (int)((q1 - q < kNu3Batch) ? (q1 - q) : kNu3Batch);
-        const bool mine = (lane >> 3) == j && (lane & 7) < cnt;
-        if (mine) {
-          dst_s[sb * kNu3Batch + (lane & 7)] = d;
-          const char* a = reinterpret_cast<const char*>(P + (int64_t)d * ldP + 3 * H);
-#pragma unroll
-          for (int l = 0; l < H * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + l * 128));
-        }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&ifull[sb]);          // the consumers start the batch's A3h gathers one batch ahead of its rows
-          mbar_arrive_expect_tx(&full[sb], (uint32_t)(cnt * C::ROW_BYTES));
-        }
-        __syncwarp();
-        if (mine)
-          bulk_copy_g2s(ring + (size_t)(sb * kNu3Batch + (lane & 7)) * C::ROW_BYTES, e16 + pos * 2 * H, C::ROW_BYTES, &full[sb]);
-      }
-    }
-    return;
-  }
-
-  // ------------------------------------------------------------------ consumers: thread = channel
-  const int t = threadIdx.x;
-  const float sc = partial_out ? 0.f : scale_h[t], sh = partial_out ? 0.f : shift_h[t];
-  const float* Pa3 = P + 3 * H + t;
-  int64_t q = q0;
-  int64_t waited = -1;                       // batch whose rows have landed
-  const int64_t nbatches = (q1 - q0 + kNu3Batch - 1) / kNu3Batch;
-  float a3[kNu3Batch], a3n[kNu3Batch];     // A3h[dst] of the current batch and of the next one (in flight)
-  auto gather_a3 = [&](int64_t b, float (&dstv)[kNu3Batch]) {
-    const int sb = (int)(b % C::NBATCH);
-    mbar_wait(&ifull[sb], (uint32_t)((b / C::NBATCH) & 1), 20, watch, watch_tag(kWkNode3, kWrEpilogue, kWbDFull), sb, b);
-    const int4 d0 = *reinterpret_cast<const int4*>(dst_s + sb * kNu3Batch), d1 = *reinterpret_cast<const int4*>(dst_s + sb * kNu3Batch + 4);
-    const int dd[kNu3Batch] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    const int cnt = (int)((q1 - q0 - b * kNu3Batch < kNu3Batch) ? (q1 - q0 - b * kNu3Batch) : kNu3Batch);
-#pragma unroll
-    for (int r = 0; r < kNu3Batch; ++r) dstv[r] = (r < cnt) ? __ldg(Pa3 + (int64_t)dd[r] * ldP) : 0.f;
-  };
-  if (nbatches > 0) gather_a3(0, a3n);
-  // node-only operands, loaded one node ahead
-  int pa = 0, pb = 0;
-  float a1 = 0.f, hin = 0.f, f0 = 0.f;
-  int64_t qb_next = g.out_ptr[n0 + 1];
-  if (!partial_out) {
-    pa = g.in_ptr[n0]; pb = g.in_ptr[n0 + 1];
-    a1 = __ldg(P + n0 * ldP + a1_off + t);
-    if (residual) hin = h_in[n0 * H + t];
-    f0 = F[n0 * H + t];
-  }
-  for (int64_t i = n0; i < n1; ++i) {
-    const int64_t qb = qb_next;
-    // prefetch the next node's operands
-    int npa = 0, npb = 0;
-    float na1 = 0.f, nhin = 0.f, nf0 = 0.f;
-    if (i + 1 < n1) {
-      qb_next = g.out_ptr[i + 2];
-      if (!partial_out) {
-        npa = pb; npb = g.in_ptr[i + 2];
-        na1 = __ldg(P + (i + 1) * ldP + a1_off + t);
-        if (residual) nhin = h_in[(i + 1) * H + t];
-        nf0 = F[(i + 1) * H + t];
-      }
-    }
-    float num = 0.f, den = 0.f;
-    while (q < qb) {
-      const int64_t k = q - q0, b = k / kNu3Batch;
-      const int sb = (int)(b % C::NBATCH);
-      if (b != waited) {                     // first touch of this batch: its gathers were started a batch ago
-#pragma unroll
-        for (int r = 0; r < kNu3Batch; ++r) a3[r] = a3n[r];
-        if (b + 1 < nbatches) gather_a3(b + 1, a3n);
-        mbar_wait(&full[sb], (uint32_t)((b / C::NBATCH) & 1), 20, watch, watch_tag(kWkNode3, kWrEpilogue, kWbFull), sb, b);
-        waited = b;
-      }
-      const int r0 = (int)(k % kNu3Batch);
-      const int r1 = (int)(((qb - q0) < (b + 1) * kNu3Batch) ? (qb - q0 - b * kNu3Batch) : kNu3Batch);   // end row (exclusive) of this node in the batch
-      const __half* row = reinterpret_cast<const __half*>(ring + (size_t)(sb * kNu3Batch) * C::ROW_BYTES) + t;
-#pragma unroll
-      for (int r = 0; r < kNu3Batch; ++r) {
-        if (r >= r0 && r < r1) {             // CTA-uniform
-          const float x = __half2float(row[r * 2 * H]) + __half2float(row[r * 2 * H + H]);   // e' / 16
-          float tt, sg;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(tt) : "f"(-16.0f * 1.4426950408889634f * x));
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + tt));
-          num = fmaf(sg, a3[r], num);
-          den += sg;
-        }
-      }
-      q = q0 + b * kNu3Batch + r1;
-      if (r1 == kNu3Batch || q == q1) {      // batch consumed: hand its slots back to the producer
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[sb]);
-      }
-    }
-    if (partial_out) {   // multi-GPU: un-normalised partial sums of a halo source node, for its owner
-      partial_out[(i - node_begin) * 2 * H + t] = num;
-      partial_out[(i - node_begin) * 2 * H + H + t] = den;
-      continue;
-    }
-    if (xp_ptr) {        // multi-GPU: partial sums other ranks computed for this node, in rank order
-      for (int r = xp_ptr[i], re = xp_ptr[i + 1]; r < re; ++r) {
-        const float* xr = xp_buf + (int64_t)xp_row[r] * 2 * H;
-        num += xr[t];
-        den += xr[H + t];
-      }
-    }
-    const float bk = gate_div(num, den);
-    // F: from the edge pass, resolving chunk-straddling segments
-    float f = 0.f;
-    if (pb > pa) {
-      const int k0 = pa / chunk, k1 = (pb - 1) / chunk;
-      if (k0 == k1) {
-        f = f0;
-      } else {
-        float fn = 0.f, fd = 0.f;
-        for (int kk = k0; kk < k1; ++kk) {
-          fn += carry[((int64_t)kk * 4 + 2) * H + t];
-          fd += carry[((int64_t)kk * 4 + 3) * H + t];
-        }
-        f = gate_div(fn + carry[((int64_t)k1 * 4 + 0) * H + t], fd + carry[((int64_t)k1 * 4 + 1) * H + t]);
-      }
-    }
-    const float u = fmaxf(fmaf(a1 + f + bk, sc, sh), 0.f) + hin;
-    h_out[i * H + t] = u;
-    if (h16_out) {
-      __half hh, ll;
-      split1(u, hh, ll);
-      h16_out[(i - node_begin) * 2 * H + t] = hh;
-      h16_out[(i - node_begin) * 2 * H + H + t] = ll;
-    }
-    pa = npa; pb = npb; a1 = na1; hin = nhin; f0 = nf0;
-  }
-}
-
 template <int H>
 static int encode2_impl(const float* in, const int32_t* idx, int64_t rows, int in_f, int hid, const float* W1,
                         const float* b1, const float* W2t, const float* b2, void* out16, float* out32,
@@ -576,32 +332,6 @@ static int node_update2_impl(const gnb_graph_t* g, const float* P, int64_t ldP, 
                              float* h_out, void* h16_out, int flags, int chunk, int64_t node_begin, int64_t node_end,
                              const int32_t* xp_ptr, const int32_t* xp_row, const float* xp_buf, float* partial_out,
                              cudaStream_t stream) {
-  static const int variant = [] { const char* v = getenv("GNB_NODE_UPDATE"); return v ? atoi(v) : 3; }();
-  const bool streams_rows = (flags & GNB_F_SYMMETRIC) || partial_out;
-  if (variant == 3 && streams_rows && g->num_edges > 0) {
-    using C = Nu3Cfg<H>;
-    auto kern = node_update3_kernel<H>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (err != cudaSuccess) {
-      set_error("gnb_node_update2: cudaFuncSetAttribute(%zu): %s", C::SMEM, cudaGetErrorString(err));
-      return (int)err;
-    }
-    static int per_sm = 0;
-    if (per_sm == 0) {
-      int n = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, C::THREADS, C::SMEM) != cudaSuccess || n < 1) n = 1;
-      per_sm = n;
-    }
-    const int64_t nodes = node_end - node_begin;
-    int64_t grid = (int64_t)sm_count() * per_sm;
-    const int64_t min_nodes = 64;                         // a CTA should have a few dozen nodes to amortise its start-up
-    if (grid > (nodes + min_nodes - 1) / min_nodes) grid = (nodes + min_nodes - 1) / min_nodes;
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(*g, P, ldP, (const __half*)e16, F, carry, h_in, scale_h, shift_h,
-                                                        h_out, (__half*)h16_out, flags, chunk, node_begin, node_end,
-                                                        xp_ptr, xp_row, xp_buf, partial_out, watch_get());
-    return check_launch(partial_out ? "gnb_reverse_partial2" : "gnb_node_update2");
-  }
   constexpr int NPB = kNu2Threads / (H / 8);
   const int64_t items = (node_end - node_begin + NPB - 1) / NPB;
   const int64_t cap = (int64_t)sm_count() * 2;   // persistent: two resident CTAs per SM, grid-stride over the nodes
