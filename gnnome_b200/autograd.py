@@ -35,6 +35,68 @@ def _call(name, device, *args):
         _lib.check(getattr(lib, name)(*args, current_stream_ptr(device)), name)
 
 
+_TC_WIDTHS = (64, 128, 256)      # contraction widths gnb_node_linear_tc2 is built for
+_pack_cache = {}                 # id(weight) -> (version, packed W, packed W^T): re-packed when the parameter changes
+
+
+def _packed(weight, transposed):
+    from . import ops
+    hit = _pack_cache.get(id(weight))
+    if hit is None or hit[0] != weight._version or hit[3] is not weight:
+        w = weight.detach().float().contiguous()
+        hit = _pack_cache[id(weight)] = (weight._version, ops.pack_linear_tc(w), ops.pack_linear_tc(w.t().contiguous()), weight)
+    return hit[2 if transposed else 1]
+
+
+class TcLinear(torch.autograd.Function):
+    """``x @ weight.T + bias`` for the training path on the tensor cores: forward and the input gradient
+    ``gx = g @ weight`` run on ``gnb_node_linear_tc2`` (tcgen05, fp16 hi/lo split operands, fp32 accumulate: fp32-level
+    accuracy) after one ``gnb_split_rows`` pass over the operand; the weight gradient
+    ``gW = g.T @ x`` (a reduction over all rows into an out x in matrix) is a library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import ops
+        x = _c(x)
+        M = weight.shape[0]
+        b = bias.detach() if bias is not None else torch.zeros(M, dtype=torch.float32, device=x.device)
+        out = ops.node_linear_tc2(ops.split_rows(x), _packed(weight, False), _c(b.float()), M)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        x, weight = ctx.saved_tensors
+        g = _c(g)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            K = weight.shape[1]
+            gx = ops.node_linear_tc2(ops.split_rows(g), _packed(weight, True),
+                                     torch.zeros(K, dtype=torch.float32, device=g.device), K)
+        if ctx.needs_input_grad[1]:
+            gw = g.t() @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb
+
+
+def linear(lin_or_weight, x, bias=None):
+    """``nn.Linear`` / ``F.linear`` of the training path: on the tensor cores where both contraction widths (in for the
+    forward, out for the input gradient) are ones the kernel is built for and there are rows to process, else
+    ``F.linear``."""
+    if isinstance(lin_or_weight, torch.nn.Linear):
+        weight, bias = lin_or_weight.weight, lin_or_weight.bias
+    else:
+        weight = lin_or_weight
+    M, K = weight.shape
+    if (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.shape[0] > 0
+            and K in _TC_WIDTHS and M in _TC_WIDTHS):
+        return TcLinear.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
 class GatherAdd3(torch.autograd.Function):
     """z[p] = A[src_p] + B[dst_p] + C[p]; A, B node tables [N][W], C edge rows [E][W] (position order)."""
 
@@ -279,14 +341,14 @@ def layer_forward(conv, gi: GraphIndex, h, e_pos):
         raise NotImplementedError(f"normalization={conv.normalization!r} (the reference itself fails on 'none': bn_e is "
                                   f"used unconditionally, gated_gcn_full.py:106)")
     sym = conv._symmetric
-    A1h, A2h = conv.A_1(h), conv.A_2(h)                                  # :91-92
-    B1h, B2h, B3e = conv.B_1(h), conv.B_2(h), conv.B_3(e_pos)            # :95-97
+    A1h, A2h = linear(conv.A_1, h), linear(conv.A_2, h)                  # :91-92
+    B1h, B2h, B3e = linear(conv.B_1, h), linear(conv.B_2, h), linear(conv.B_3, e_pos)   # :95-97
     z = GatherAdd3.apply(gi, B1h, B2h, B3e)                              # :104-105
     ehat = normalize(conv.bn_e, z, conv.training, updates=2 if sym else 1)    # :106 (+ :119 on the reversed graph)
     e_new, sigma = Gate.apply(ehat, e_pos if conv.residual else None)    # :107-111
     u = A1h + Agg.apply(gi, A2h, sigma, 0)                               # :112-114
     if sym:
-        u = u + Agg.apply(gi, conv.A_3(h), sigma, 1)                     # :93, :125-127 (same sigma)
+        u = u + Agg.apply(gi, linear(conv.A_3, h), sigma, 1)             # :93, :125-127 (same sigma)
     u = normalize(conv.bn_h, u, conv.training)                           # :131-132
     h_new = torch.relu(u)                                                # :134
     if conv.residual:
@@ -301,7 +363,7 @@ def predictor_forward(pred, gi: GraphIndex, x, e_pos):
     W1, b1 = pred.W1.weight, pred.W1.bias
     S1 = F.linear(x, W1[:, :H])
     S2 = F.linear(x, W1[:, H:2 * H], b1)
-    E1 = F.linear(e_pos, W1[:, 2 * H:])
+    E1 = F.linear(e_pos, W1[:, 2 * H:])      # W1 column blocks are views (a packed copy per step would need its own cache)
     hid = torch.relu(GatherAdd3.apply(gi, S1, S2, E1))
     return pred.W3(torch.relu(pred.W2(hid)))                             # [E][1], position order
 

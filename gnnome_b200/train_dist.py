@@ -202,6 +202,9 @@ class CudaPrims:
     def layer_norm(self, norm, x):
         return self.A.LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
 
+    def linear(self, lin, x):
+        return self.A.linear(lin, x)
+
 
 # ------------------------------------------------------------------------------------------------
 # the sharded training step
@@ -270,14 +273,14 @@ class ShardedTrainer:
         p, gi, sh = self.p, self.gi, self.shard
         n_own, H = sh.n_own, conv.out_channels
         h_loc = self._with_halo(h_own)
-        A1h, A2h = conv.A_1(h_own), conv.A_2(h_loc)                                            # :91-92
-        B1h, B2h, B3e = conv.B_1(h_loc), conv.B_2(h_loc), conv.B_3(e)                          # :95-97
+        A1h, A2h = p.linear(conv.A_1, h_own), p.linear(conv.A_2, h_loc)                        # :91-92
+        B1h, B2h, B3e = p.linear(conv.B_1, h_loc), p.linear(conv.B_2, h_loc), p.linear(conv.B_3, e)   # :95-97
         z = p.gather_add3(gi, B1h, B2h, B3e)                                                   # :104-105
         ehat = self._norm(conv.bn_e, z, self.e_global, 2 if conv._symmetric else 1, first)    # :106 (+ :119)
         e_new, sigma = p.gate(ehat, e if conv.residual else None)                              # :107-111
         u = A1h + p.agg_in(gi, A2h, sigma)[:n_own]                                             # :112-114
         if conv._symmetric:                                                                    # :93, :125-127
-            nd = torch.cat(p.agg_out_raw(gi, conv.A_3(h_loc), sigma), 1)                       # [n_local][2H], local edges
+            nd = torch.cat(p.agg_out_raw(gi, p.linear(conv.A_3, h_loc), sigma), 1)             # [n_local][2H], local edges
             tot = nd[:n_own]
             if self.plan.active:
                 tot = tot + HaloScatterAdd.apply(self.ex, nd[n_own:])                          # partial sums of remote sources
