@@ -341,14 +341,16 @@ def layer_forward(conv, gi: GraphIndex, h, e_pos):
         raise NotImplementedError(f"normalization={conv.normalization!r} (the reference itself fails on 'none': bn_e is "
                                   f"used unconditionally, gated_gcn_full.py:106)")
     sym = conv._symmetric
-    A1h, A2h = linear(conv.A_1, h), linear(conv.A_2, h)                  # :91-92
-    B1h, B2h, B3e = linear(conv.B_1, h), linear(conv.B_2, h), linear(conv.B_3, e_pos)   # :95-97
+    # library GEMMs here: this single-GPU path is pinned to the reference's training fixture, whose gradients sit on
+    # ReLU kinks; the sharded trainer (train_dist.py) runs its Linears on the tensor cores
+    A1h, A2h = conv.A_1(h), conv.A_2(h)                                  # :91-92
+    B1h, B2h, B3e = conv.B_1(h), conv.B_2(h), conv.B_3(e_pos)            # :95-97
     z = GatherAdd3.apply(gi, B1h, B2h, B3e)                              # :104-105
     ehat = normalize(conv.bn_e, z, conv.training, updates=2 if sym else 1)    # :106 (+ :119 on the reversed graph)
     e_new, sigma = Gate.apply(ehat, e_pos if conv.residual else None)    # :107-111
     u = A1h + Agg.apply(gi, A2h, sigma, 0)                               # :112-114
     if sym:
-        u = u + Agg.apply(gi, linear(conv.A_3, h), sigma, 1)             # :93, :125-127 (same sigma)
+        u = u + Agg.apply(gi, conv.A_3(h), sigma, 1)                     # :93, :125-127 (same sigma)
     u = normalize(conv.bn_h, u, conv.training)                           # :131-132
     h_new = torch.relu(u)                                                # :134
     if conv.residual:

@@ -20,6 +20,7 @@ namespace gnb {
 namespace train {
 
 constexpr int kT = 256;
+constexpr int kB = 4;     // edge rows in flight per thread in the per-node loops
 
 static unsigned blocks_for(int64_t items) {
   int64_t b = (items + kT - 1) / kT, cap = (int64_t)sm_count() * 16;
@@ -58,12 +59,19 @@ __global__ void seg_sum_kernel(gnb_graph_t g, int H, const float* __restrict__ X
   for (int64_t k = (int64_t)blockIdx.x * kT + threadIdx.x; k < total; k += (int64_t)gridDim.x * kT) {
     const int64_t i = k / h4;
     const int c = (int)(k - i * h4) * 4;
+    // kB edge rows in flight per thread (a loop with one dependent load per trip ran at ~1 TB/s); same summation order
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mode == 0) {
-      for (int p = g.in_ptr[i], pe = g.in_ptr[i + 1]; p < pe; ++p) acc = add4(acc, ld4(X + (int64_t)p * H + c));
-    } else {
-      for (int q = g.out_ptr[i], qe = g.out_ptr[i + 1]; q < qe; ++q)
-        acc = add4(acc, ld4(X + (int64_t)g.out_pos[q] * H + c));
+    const int a0 = mode == 0 ? g.in_ptr[i] : g.out_ptr[i], a1 = mode == 0 ? g.in_ptr[i + 1] : g.out_ptr[i + 1];
+    for (int p0 = a0; p0 < a1; p0 += kB) {
+      int64_t row[kB];
+      float4 v[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) row[u] = (p0 + u < a1) ? (mode == 0 ? (int64_t)(p0 + u) : (int64_t)g.out_pos[p0 + u]) : -1;
+#pragma unroll
+      for (int u = 0; u < kB; ++u) v[u] = row[u] >= 0 ? ld4(X + row[u] * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kB; ++u)
+        if (row[u] >= 0) acc = add4(acc, v[u]);
     }
     st4(out + i * ldo + c, acc);
   }
@@ -81,17 +89,29 @@ __global__ void agg_fwd_kernel(gnb_graph_t g, int H, const float* __restrict__ A
     const int64_t i = k / h4;
     const int c = (int)(k - i * h4) * 4;
     float4 num = make_float4(0.f, 0.f, 0.f, 0.f), dn = num;
-    if (mode == 0) {
-      for (int p = g.in_ptr[i], pe = g.in_ptr[i + 1]; p < pe; ++p) {
-        const float4 s = ld4(sigma + (int64_t)p * H + c);
-        num = fma4(s, ld4(A + (int64_t)g.in_src[p] * ldA + c), num);
-        dn = add4(dn, s);
+    const int a0 = mode == 0 ? g.in_ptr[i] : g.out_ptr[i], a1 = mode == 0 ? g.in_ptr[i + 1] : g.out_ptr[i + 1];
+    for (int p0 = a0; p0 < a1; p0 += kB) {   // indices, then rows, then arithmetic: kB rows in flight, same order
+      int64_t row[kB], nb[kB];
+      float4 sv[kB], av[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const bool ok = p0 + u < a1;
+        row[u] = ok ? (mode == 0 ? (int64_t)(p0 + u) : (int64_t)g.out_pos[p0 + u]) : -1;
+        nb[u] = ok ? (mode == 0 ? (int64_t)g.in_src[p0 + u] : (int64_t)g.out_dst[p0 + u]) : 0;
       }
-    } else {
-      for (int q = g.out_ptr[i], qe = g.out_ptr[i + 1]; q < qe; ++q) {
-        const float4 s = ld4(sigma + (int64_t)g.out_pos[q] * H + c);
-        num = fma4(s, ld4(A + (int64_t)g.out_dst[q] * ldA + c), num);
-        dn = add4(dn, s);
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        if (row[u] >= 0) {
+          sv[u] = ld4(sigma + row[u] * H + c);
+          av[u] = ld4(A + nb[u] * ldA + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        if (row[u] >= 0) {
+          num = fma4(sv[u], av[u], num);
+          dn = add4(dn, sv[u]);
+        }
       }
     }
     st4(den + i * H + c, dn);
@@ -143,27 +163,37 @@ __global__ void agg_bwd_node_kernel(gnb_graph_t g, int H, const float* __restric
     const int64_t n = k / h4;
     const int c = (int)(k - n * h4) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mode == 0) {   // forward aggregated over in-edges with neighbour = src: n is the SOURCE of these edges
-      for (int q = g.out_ptr[n], qe = g.out_ptr[n + 1]; q < qe; ++q) {
-        const int64_t p = g.out_pos[q], i = g.out_dst[q];
-        const float4 go = ld4(gout + i * H + c), s = ld4(sigma + p * H + c);
-        if (raw) { acc = fma4(go, s, acc); continue; }
-        const float4 d = ld4(den + i * H + c);
-        acc.x = fmaf(go.x / (d.x + kGateEps), s.x, acc.x);
-        acc.y = fmaf(go.y / (d.y + kGateEps), s.y, acc.y);
-        acc.z = fmaf(go.z / (d.z + kGateEps), s.z, acc.z);
-        acc.w = fmaf(go.w / (d.w + kGateEps), s.w, acc.w);
+    // mode 0: the forward aggregated over in-edges with neighbour = src, so n is the SOURCE of the edges walked here
+    // (src-CSR: row = out_pos[q], owner i = out_dst[q]); mode 1: n is the DESTINATION (dst-CSR: row = p, i = in_src[p]).
+    const int a0 = mode == 0 ? g.out_ptr[n] : g.in_ptr[n], a1 = mode == 0 ? g.out_ptr[n + 1] : g.in_ptr[n + 1];
+    for (int p0 = a0; p0 < a1; p0 += kB) {   // kB rows in flight, same summation order
+      int64_t row[kB], own[kB];
+      float4 gv[kB], sv[kB], dv[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const bool ok = p0 + u < a1;
+        row[u] = ok ? (mode == 0 ? (int64_t)g.out_pos[p0 + u] : (int64_t)(p0 + u)) : -1;
+        own[u] = ok ? (mode == 0 ? (int64_t)g.out_dst[p0 + u] : (int64_t)g.in_src[p0 + u]) : 0;
       }
-    } else {           // forward aggregated over out-edges with neighbour = dst: n is the DESTINATION
-      for (int p = g.in_ptr[n], pe = g.in_ptr[n + 1]; p < pe; ++p) {
-        const int64_t i = g.in_src[p];
-        const float4 go = ld4(gout + i * H + c), s = ld4(sigma + (int64_t)p * H + c);
-        if (raw) { acc = fma4(go, s, acc); continue; }
-        const float4 d = ld4(den + i * H + c);
-        acc.x = fmaf(go.x / (d.x + kGateEps), s.x, acc.x);
-        acc.y = fmaf(go.y / (d.y + kGateEps), s.y, acc.y);
-        acc.z = fmaf(go.z / (d.z + kGateEps), s.z, acc.z);
-        acc.w = fmaf(go.w / (d.w + kGateEps), s.w, acc.w);
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        if (row[u] >= 0) {
+          gv[u] = ld4(gout + own[u] * H + c);
+          sv[u] = ld4(sigma + row[u] * H + c);
+          if (!raw) dv[u] = ld4(den + own[u] * H + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        if (row[u] < 0) continue;
+        if (raw) {
+          acc = fma4(gv[u], sv[u], acc);
+        } else {
+          acc.x = fmaf(gv[u].x / (dv[u].x + kGateEps), sv[u].x, acc.x);
+          acc.y = fmaf(gv[u].y / (dv[u].y + kGateEps), sv[u].y, acc.y);
+          acc.z = fmaf(gv[u].z / (dv[u].z + kGateEps), sv[u].z, acc.z);
+          acc.w = fmaf(gv[u].w / (dv[u].w + kGateEps), sv[u].w, acc.w);
+        }
       }
     }
     st4(gA + n * ldg + c, acc);
