@@ -51,10 +51,10 @@ SIGNATURES = {
     'gnb_reverse_partial': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _L, _L, _P, _P]),
     'gnb_score_forward': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'gnb_split16_bytes': (_S, [_L, _I]),
-    'gnb_split_rows': (_I, [_P, _P, _L, _I, _P, _P]),
+    'gnb_split_rows': (_I, [_P, _P, _L, _I, _P, _P, _P]),
     'gnb_merge_rows': (_I, [_P, _P, _L, _I, _P, _P]),
     'gnb_encode2': (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
-    'gnb_node_linear_tc2': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P]),
+    'gnb_node_linear_tc2': (_I, [_P, _L, _I, _P, _P, _I, _P, _L, _P, _P]),
     'gnb_edge_tile_tc2': (_I, [_I]),
     'gnb_edge_chunk_tc2': (_I, [_I]),
     'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _I, _P]),
@@ -90,7 +90,7 @@ SIGNATURES = {
     'gnb_walk_jumped_nodes': (_I, [ctypes.POINTER(GnbWalkGraph), ctypes.POINTER(GnbWalkGraph), _P, _L, _P]),
 }
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 GNB_F_SYMMETRIC = 1
 GNB_F_RESIDUAL = 2
 

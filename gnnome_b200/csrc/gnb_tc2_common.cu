@@ -101,7 +101,8 @@ __global__ void pack_linear_tc_kernel(const float* __restrict__ W, int M, int K,
 
 // out16[r][:] = split(in[idx ? idx[r] : r][:]); one thread per 8 consecutive channels
 __global__ void split_rows_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx, int64_t rows, int K,
-                                  __half* __restrict__ out) {
+                                  __half* __restrict__ out, const float* __restrict__ scale) {
+  const float xs = kXScale * (scale ? *scale : 1.f);   // optional per-tensor pre-scale (a power of two: exact)
   const int k8 = K / 8;
   const int64_t total = rows * k8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -110,8 +111,7 @@ __global__ void split_rows_kernel(const float* __restrict__ in, const int32_t* _
     const int64_t rs = idx ? (int64_t)idx[r] : r;
     const float4 a = *reinterpret_cast<const float4*>(in + rs * K + c);
     const float4 b = *reinterpret_cast<const float4*>(in + rs * K + c + 4);
-    float x[8] = {a.x * kXScale, a.y * kXScale, a.z * kXScale, a.w * kXScale,
-                  b.x * kXScale, b.y * kXScale, b.z * kXScale, b.w * kXScale};
+    float x[8] = {a.x * xs, a.y * xs, a.z * xs, a.w * xs, b.x * xs, b.y * xs, b.z * xs, b.w * xs};
     uint4 h, l;
     split8(x, h, l);
     *reinterpret_cast<uint4*>(out + r * 2 * K + c) = h;
@@ -199,12 +199,13 @@ static unsigned stream_blocks(int64_t total) {
   return (unsigned)(b < 1 ? 1 : (b < cap ? b : cap));
 }
 
-extern "C" int gnb_split_rows(const float* in, const int32_t* idx, int64_t rows, int K, void* out16, void* stream) {
+extern "C" int gnb_split_rows(const float* in, const int32_t* idx, int64_t rows, int K, void* out16, const float* scale,
+                              void* stream) {
   GNB_REQUIRE(K > 0 && K % 8 == 0, "gnb_split_rows: K=%d must be a positive multiple of 8", K);
   if (rows == 0) return 0;
   GNB_REQUIRE(in && out16, "null pointer");
   GNB_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)out16 % 16 == 0), "gnb_split_rows: pointers must be 16-byte aligned");
-  tc::split_rows_kernel<<<stream_blocks(rows * (K / 8)), 256, 0, (cudaStream_t)stream>>>(in, idx, rows, K, (__half*)out16);
+  tc::split_rows_kernel<<<stream_blocks(rows * (K / 8)), 256, 0, (cudaStream_t)stream>>>(in, idx, rows, K, (__half*)out16, scale);
   return check_launch("gnb_split_rows");
 }
 

@@ -35,7 +35,8 @@ struct Lin2Cfg {
 template <int K, bool kMC>
 __global__ void __launch_bounds__(kLin2Threads, 1)
 node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, const __half* __restrict__ Wp, const float* __restrict__ bias, int M,
-                       float* __restrict__ out, int64_t ld_out, int nblk, int workers, const Watch watch) {
+                       float* __restrict__ out, int64_t ld_out, int nblk, int workers, const Watch watch,
+                       const float* __restrict__ out_scale) {
   using C = Lin2Cfg<K>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -123,6 +124,7 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
     const int ch = cb * kM + q * 32 + lane;
     const bool ch_ok = ch < M;
     const float b = ch_ok ? bias[ch] : 0.f;
+    const float os = out_scale ? *out_scale : 1.f;   // optional per-tensor post-scale (undoes a pre-scale of X)
     int i = 0;
     for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
       if ((i & 1) != g) continue;
@@ -141,17 +143,17 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
         float* o = out + r0 * ld_out + ch;
         if (r0 + kLin2NT <= rows) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j * ld_out] = __uint_as_float(v0[j]) + b;
+          for (int j = 0; j < 32; ++j) o[j * ld_out] = fmaf(__uint_as_float(v0[j]), os, b);
           o += 32 * ld_out;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j * ld_out] = __uint_as_float(v1[j]) + b;
+          for (int j = 0; j < 32; ++j) o[j * ld_out] = fmaf(__uint_as_float(v1[j]), os, b);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (r0 + j < rows) o[j * ld_out] = __uint_as_float(v0[j]) + b;
+            if (r0 + j < rows) o[j * ld_out] = fmaf(__uint_as_float(v0[j]), os, b);
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (r0 + 32 + j < rows) o[(32 + j) * ld_out] = __uint_as_float(v1[j]) + b;
+            if (r0 + 32 + j < rows) o[(32 + j) * ld_out] = fmaf(__uint_as_float(v1[j]), os, b);
         }
       }
     }
@@ -164,7 +166,7 @@ node_linear_tc2_kernel(const __grid_constant__ CUtensorMap map_x, int64_t rows, 
 
 template <int K>
 static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, const float* bias, int M, float* out,
-                                int64_t ld_out, cudaStream_t stream) {
+                                int64_t ld_out, const float* out_scale, cudaStream_t stream) {
   using C = Lin2Cfg<K>;
   const int nblk_ = (M + kM - 1) / kM;
   const bool mc = nblk_ % 2 == 0;
@@ -195,7 +197,8 @@ static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, map_x, rows, (const __half*)Wp, bias, M, out, ld_out, nblk, workers, watch_get());
+  e = cudaLaunchKernelEx(&cfg, kern, map_x, rows, (const __half*)Wp, bias, M, out, ld_out, nblk, workers, watch_get(),
+                         out_scale);
   if (e != cudaSuccess) {
     set_error("gnb_node_linear_tc2: launch failed: %s", cudaGetErrorString(e));
     return (int)e;
@@ -209,16 +212,16 @@ static int node_linear_tc2_impl(const void* X16, int64_t rows, const void* Wp, c
 using namespace gnb;
 
 extern "C" int gnb_node_linear_tc2(const void* X16, int64_t rows, int K, const void* Wp, const float* bias, int M,
-                                   float* out, int64_t ld_out, void* stream) {
+                                   float* out, int64_t ld_out, const float* out_scale, void* stream) {
   GNB_REQUIRE(M > 0 && ld_out >= M, "gnb_node_linear_tc2: bad output shape (M=%d ld=%lld)", M, (long long)ld_out);
   if (rows == 0) return 0;
   GNB_REQUIRE(X16 && Wp && bias && out, "null pointer");
   GNB_REQUIRE(((uintptr_t)X16 % 16 == 0) && ((uintptr_t)Wp % 16 == 0), "gnb_node_linear_tc2: X16 / Wp must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   switch (K) {
-    case 64: return tc::node_linear_tc2_impl<64>(X16, rows, Wp, bias, M, out, ld_out, s);
-    case 128: return tc::node_linear_tc2_impl<128>(X16, rows, Wp, bias, M, out, ld_out, s);
-    case 256: return tc::node_linear_tc2_impl<256>(X16, rows, Wp, bias, M, out, ld_out, s);
+    case 64: return tc::node_linear_tc2_impl<64>(X16, rows, Wp, bias, M, out, ld_out, out_scale, s);
+    case 128: return tc::node_linear_tc2_impl<128>(X16, rows, Wp, bias, M, out, ld_out, out_scale, s);
+    case 256: return tc::node_linear_tc2_impl<256>(X16, rows, Wp, bias, M, out, ld_out, out_scale, s);
   }
   set_error("gnb_node_linear_tc2: K=%d unsupported (64, 128, 256)", K);
   return GNB_E_INVALID;

@@ -191,16 +191,17 @@ def empty_split16(rows, K, device):
     return torch.empty((rows, 2, K), dtype=torch.float16, device=device)
 
 
-def split_rows(x, idx=None, out=None):
-    """fp32 rows -> split16 images; ``out[r] = split(x[idx[r]])`` when ``idx`` is given."""
+def split_rows(x, idx=None, out=None, scale=None):
+    """fp32 rows -> split16 images; ``out[r] = split(x[idx[r]])`` when ``idx`` is given; ``scale``: optional 0-dim float32
+    CUDA tensor multiplied in before the split (a power of two, see the header)."""
     lib = _lib.load()
     rows = x.shape[0] if idx is None else idx.numel()
     K = x.shape[1]
     if out is None:
         out = empty_split16(rows, K, x.device)
     with _logged('gnb_split_rows', x.device):
-        _lib.check(lib.gnb_split_rows(_f32(x, 'x'), _opt(idx), rows, K, _img(out, 'out'), current_stream_ptr(x.device)),
-                   'gnb_split_rows')
+        _lib.check(lib.gnb_split_rows(_f32(x, 'x'), _opt(idx), rows, K, _img(out, 'out'), _opt(scale),
+                                      current_stream_ptr(x.device)), 'gnb_split_rows')
     return out
 
 
@@ -230,16 +231,17 @@ def encode2(x, idx, W1, b1, W2t, b2, rows, want16=True, want32=False):
     return out16, out32
 
 
-def node_linear_tc2(x16, Wp, bias, M, out=None):
-    """out = X @ W.T + bias with X in split16 format; Wp = pack_linear_tc(W[M][K])."""
+def node_linear_tc2(x16, Wp, bias, M, out=None, out_scale=None):
+    """out = out_scale * (X @ W.T) + bias with X in split16 format; Wp = pack_linear_tc(W[M][K]); ``out_scale``: optional
+    0-dim float32 CUDA tensor."""
     lib = _lib.load()
     rows, _, K = x16.shape
     if out is None:
         out = torch.empty((rows, M), dtype=torch.float32, device=x16.device)
     with _logged('gnb_node_linear_tc2', x16.device):
         _lib.check(lib.gnb_node_linear_tc2(_img(x16, 'x16'), rows, K, Wp.data_ptr(), _f32(bias, 'bias'), M,
-                                           _f32(out, 'out'), out.stride(0), current_stream_ptr(x16.device)),
-                   'gnb_node_linear_tc2')
+                                           _f32(out, 'out'), out.stride(0), _opt(out_scale),
+                                           current_stream_ptr(x16.device)), 'gnb_node_linear_tc2')
     return out
 
 

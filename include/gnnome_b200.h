@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNB_ABI_VERSION 10
+#define GNB_ABI_VERSION 11
 
 #define GNB_E_INVALID   (-1)  /* bad argument (shape, alignment, unsupported H) */
 #define GNB_E_WORKSPACE (-2)  /* workspace too small */
@@ -170,9 +170,12 @@ int gnb_scatter_rows(const float* in, const int32_t* idx, int64_t rows, int W, f
 /* Bytes of the split16 form of a [rows][K] matrix. */
 size_t gnb_split16_bytes(int64_t rows, int K);
 
-/* out16[r] = split(in[idx ? idx[r] : r])   (fp32 rows -> images; idx = gnb_graph_t.in_eid moves edge rows from
- * edge-id order to dst-sorted position order).  K % 8 == 0. */
-int gnb_split_rows(const float* in, const int32_t* idx, int64_t rows, int K, void* out16, void* stream);
+/* out16[r] = split(scale * in[idx ? idx[r] : r])   (fp32 rows -> images; idx = gnb_graph_t.in_eid moves edge rows from
+ * edge-id order to dst-sorted position order).  K % 8 == 0.  scale: optional DEVICE scalar (NULL = 1); the training
+ * path passes a power of two that brings a gradient tensor into the range the fp16 pair resolves (|x| ~ 2^-4 .. 2^16)
+ * and undoes it with gnb_node_linear_tc2's out_scale -- gradients are ~1 / E small, activations are O(1). */
+int gnb_split_rows(const float* in, const int32_t* idx, int64_t rows, int K, void* out16, const float* scale,
+                   void* stream);
 /* out[idx ? idx[r] : r] = merge(in16[r])   (images -> fp32 rows). */
 int gnb_merge_rows(const void* in16, const int32_t* idx, int64_t rows, int K, float* out, void* stream);
 
@@ -183,9 +186,10 @@ int gnb_encode2(const float* in, const int32_t* idx, int64_t rows, int in_f, int
                 float* out32, void* stream);
 
 /* gnb_node_linear on the tensor cores: X given as split16 images, the weight as gnb_pack_linear_tc(W[M][K]) output
- * (gated_gcn_full.py:91-96, score_predictor.py:13-14).  K in {64, 128, 256}. */
+ * (gated_gcn_full.py:91-96, score_predictor.py:13-14).  K in {64, 128, 256}.  out = out_scale * (X W^T) + bias with
+ * out_scale an optional DEVICE scalar (NULL = 1). */
 int gnb_node_linear_tc2(const void* X16, int64_t rows, int K, const void* Wp, const float* bias, int M,
-                        float* out, int64_t ld_out, void* stream);
+                        float* out, int64_t ld_out, const float* out_scale, void* stream);
 
 /* Edges per tile and carry granularity (edges per aggregation chunk) of gnb_edge_forward_tc2. */
 int gnb_edge_tile_tc2(int H);
