@@ -268,7 +268,7 @@ def test_sharded_trainer_world1_matches_the_model_training_path(gnb, kind):
         scale = max(float(q.grad.abs().max()), 1e-6)
         assert float((p.grad - q.grad).abs().max()) <= 1e-5 * scale + 1e-7, k
     for (k, b), (_, c) in zip(model.named_buffers(), ref.named_buffers()):
-        torch.testing.assert_close(b, c, rtol=1e-6, atol=1e-7, msg=k)
+        torch.testing.assert_close(b, c, rtol=1e-4, atol=1e-5, msg=k)   # tensor-core vs library Linears in the forward
     # a second step with the check-point switched off gives the same loss as with it (same parameters)
     tr2 = train_dist.ShardedTrainer(copy.deepcopy(ref), src, dst, n, x, e, y, 0, 1, torch.device('cuda'), pos_weight=1 / 3,
                                     checkpoint=False)
