@@ -435,23 +435,14 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           }
         }
       };
-      uint32_t nz[4], ne[4] = {0u, 0u, 0u, 0u};   // accumulator columns of the NEXT half batch, in flight
       auto compute = [&](auto full_tag, int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
         constexpr bool kFullChunk = decltype(full_tag)::value;   // all 32 edges exist: no per-edge validity tests
 #pragma unroll
         for (int hb = 0; hb < kEB; hb += 4) {
-          // the accumulator columns of this half batch were requested while the previous one was computed
+          uint32_t zr[4], er[4] = {0u, 0u, 0u, 0u};
+          tmem_ld4(taddr + b * kEB + hb, zr);
+          if (kResidual) tmem_ld4(taddr + kE2NT + b * kEB + hb, er);   // e / 16 = hi + lo, exact
           tmem_ld_wait();
-          uint32_t zr[4], er[4];
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            zr[w] = nz[w];
-            er[w] = ne[w];
-          }
-          if (b * kEB + hb + 4 < kE2Chunk) {
-            tmem_ld4(taddr + b * kEB + hb + 4, nz);
-            if (kResidual) tmem_ld4(taddr + kE2NT + b * kEB + hb + 4, ne);   // e / 16 = hi + lo, exact
-          }
           float v[4], sg[4];
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -497,8 +488,6 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       mbar_wait(&dfull[grp], jj & 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbDFull), grp, i);
       tc_fence_after();
       const long long t3 = kTiming ? clock64() : 0;
-      tmem_ld4(taddr, nz);
-      if (kResidual) tmem_ld4(taddr + kE2NT, ne);
       auto run_chunk = [&](auto full_tag) {
 #pragma unroll 1
         for (int b = 0; b < kE2Chunk / kEB; b += 2) {
