@@ -66,7 +66,7 @@ constexpr int kWatchWords = 8;
 constexpr unsigned long long kWatchMagic = 0x474e42484e47ull;   // "GNBHNG"
 enum WatchKernel : uint32_t { kWkEdge2 = 1, kWkLinear2 = 2, kWkScore2 = 3 };
 enum WatchRole : uint32_t { kWrProducer = 1, kWrMma = 2, kWrStore = 3, kWrEpilogue = 4 };
-enum WatchBar : uint32_t { kWbFull = 1, kWbEmpty = 2, kWbDFull = 3, kWbDEmpty = 4, kWbSFull = 5 };
+enum WatchBar : uint32_t { kWbFull = 1, kWbEmpty = 2, kWbDFull = 3, kWbDEmpty = 4, kWbOFull = 5, kWbOEmpty = 6, kWbIFull = 7 };
 __host__ __device__ constexpr uint32_t watch_tag(uint32_t kernel, uint32_t role, uint32_t bar) {
   return (kernel << 16) | (role << 8) | bar;
 }

@@ -157,7 +157,7 @@ extern "C" void gnb_set_spin_timeout_ms(long long ms) {
 extern "C" int gnb_hang_report(char* buf, size_t cap) {
   static const char* kKernel[] = {"?", "gnb_edge_forward_tc2", "gnb_node_linear_tc2", "gnb_score_forward_tc2"};
   static const char* kRole[] = {"?", "producer", "mma", "store", "epilogue"};
-  static const char* kBar[] = {"?", "full", "empty", "dfull", "dempty", "sfull"};
+  static const char* kBar[] = {"?", "full", "empty", "dfull", "dempty", "ofull", "oempty", "ifull"};
   const volatile unsigned long long* r = tc::g_watch_rec;
   if (r == nullptr || r[0] != tc::kWatchMagic) {
     if (buf != nullptr && cap > 0) buf[0] = 0;
@@ -170,7 +170,7 @@ extern "C" int gnb_hang_report(char* buf, size_t cap) {
              "device spin timed out: kernel %s, block %u, thread %u (warp %u, role %s) waited %.1f ms for barrier %s[%u] "
              "parity %u at tile iteration %lld",
              kKernel[k < 4 ? k : 0], (unsigned)(r[2] >> 32), (unsigned)(r[2] & 0xffffffffu),
-             (unsigned)(r[2] & 0xffffffffu) / 32, kRole[role < 5 ? role : 0], (double)r[5] * 1e-6, kBar[bar < 6 ? bar : 0],
+             (unsigned)(r[2] & 0xffffffffu) / 32, kRole[role < 5 ? role : 0], (double)r[5] * 1e-6, kBar[bar < 8 ? bar : 0],
              (unsigned)(r[3] >> 32), (unsigned)(r[3] & 0xffffffffu), (long long)r[4]);
   return 1;
 }

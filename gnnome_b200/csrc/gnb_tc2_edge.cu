@@ -356,7 +356,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           guard = SpinGuard();
         } else {
           __nanosleep(32);
-          guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbSFull), (uint32_t)g0, (uint32_t)((it[0] / kE2Groups) & 1), it[0]);
+          guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbOFull), (uint32_t)g0, (uint32_t)((it[0] / kE2Groups) & 1), it[0]);
         }
       }
       tma_store_wait_all();
@@ -389,7 +389,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       const long long t0 = kTiming ? clock64() : 0;
       const int slot = jj % kE2IdxSlots;
       mbar_wait(&ifull[grp * kE2IdxSlots + slot], (jj / kE2IdxSlots) & 1, 32, watch,
-                watch_tag(kWkEdge2, kWrEpilogue, kWbFull), grp * kE2IdxSlots + slot, i);
+                watch_tag(kWkEdge2, kWrEpilogue, kWbIFull), grp * kE2IdxSlots + slot, i);
       const long long t1 = kTiming ? clock64() : 0;
       const int* ia = idx_area + (grp * kE2IdxSlots + slot) * kE2IdxInts;
       const int my_dst = ia[kE2NT + lane];
@@ -514,7 +514,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       // transposed into the group's output buffer: edge row T, channels 16 hl + 8 a + [0, 8) = one 16-byte swizzle chunk.
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       // the buffer still holds the group's previous tile until the store thread has handed it back
-      mbar_wait(&oempty[grp], (jj & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbEmpty), grp, i);
+      mbar_wait(&oempty[grp], (jj & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbOEmpty), grp, i);
 #pragma unroll
       for (int hl = 0; hl < 2; ++hl) {
         uint32_t fr[16];

@@ -10,6 +10,7 @@ exporter from ``.dgl``); successors / predecessors / edge ids come from the refe
 ``{data_path}/{assembler}/info/{idx}_succ.pkl``, ``_pred.pkl``, ``_edges.pkl`` (:447-455).  Turning walks into contig
 sequences (``utils/evaluate.py``; needs the reads and Biopython) is not part of this package."""
 import os
+import shutil
 import pickle
 import random
 
@@ -67,9 +68,15 @@ def inference(data_path, model_path, assembler, savedir, device=None, dropout=No
         succs, preds, edges = (pickle.load(open(f'{info}_{name}.pkl', 'rb')) for name in ('succ', 'pred', 'edges'))  # :447-455
         prefix = g.edata['prefix_length']
         g.edata['prefix_length'] = prefix.masked_fill(prefix < 0, 0)    # :461: negative prefixes break the contig lengths
+        # One check-point directory PER GRAPH, removed once the graph's walks are written: the reference keeps a single
+        # {savedir}/checkpoint/checkpoint.pkl for the whole dataset (inference.py:398), so graph k + 1 (or a re-run)
+        # would resume from graph k's walks and visited set.
+        graph_ckpt = os.path.join(checkpoint_dir, str(idx))
+        os.makedirs(graph_ckpt, exist_ok=True)
         walks = get_contigs_greedy(g, succs, preds, edges, hp['len_threshold'], hp['num_decoding_paths'],
-                                   hp['decode_with_labels'], checkpoint_dir, hp['load_checkpoint'], threads, fast_sampling)
+                                   hp['decode_with_labels'], graph_ckpt, hp['load_checkpoint'], threads, fast_sampling)
         with open(os.path.join(inference_dir, f'{idx}_walks.pkl'), 'wb') as f:
             pickle.dump(walks, f)                                        # :472-473
+        shutil.rmtree(graph_ckpt, ignore_errors=True)
         all_walks[idx] = walks
     return all_walks
