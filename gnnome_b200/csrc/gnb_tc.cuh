@@ -37,13 +37,32 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// non-blocking test: has the phase with this parity completed?
+// Has the phase with this parity completed?  NOT a cheap probe: try_wait suspends the warp until the phase completes
+// or a system time limit expires -- about 7.5k cycles on this part, and a suspendTimeHint does not shorten it
+// (tools/microbench/trywait_probe.cu, profiles/r02h_trywait_probe.txt); a waiter wakes ~130 cycles after the arrive.
+// That makes it the right instruction for waiting on ONE barrier (a wait of a pipeline stage costs one or two polls)
+// and the wrong one for polling several: use mbar_poll there.
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+// returns at once
+__device__ __forceinline__ bool mbar_poll(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(done)

@@ -17,8 +17,9 @@
 //   warp 0      : producer.  TMA loads of the tile's operand images into input stage i % NB (the loads run NB tiles
 //                 ahead of the tensor core), the tile's (src, dst) indices into the group's index slot, L2 prefetch
 //                 of the node rows the epilogue will gather.
-//   warp 1      : MMA issue (one lane): 3 K/16 split products into the group's accumulator set + 2 HC/16 identity
-//                 products for the residual; the commit RELEASES THE INPUT STAGE -- nothing but the tensor core
+//   warps 1, 3  : MMA issue (one lane each; warp 1 the even tiles of the CTA, warp 3 the odd ones): 3 K/16 split products
+//                 into the group's accumulator set + 2 HC/16 identity products for the residual, descriptors advanced
+//                 from one base per tile; the commit RELEASES THE INPUT STAGE -- nothing but the tensor core
 //                 reads a stage, so the load pipeline is as deep as the stage ring (with the in-place stage of
 //                 round 1 / 2a, held from load to store, four of five stages sat under the epilogue groups and a
 //                 third of the epilogue's time was spent waiting for the next tile: profiles/r02b).
@@ -32,7 +33,7 @@
 //                 consecutive edges of one channel), splits the pairs into fp16 (hi, lo) with packed conversions and
 //                 stores 8 x 8 blocks TRANSPOSED into the group's OUTPUT BUFFER with stmatrix -- 16-byte rows of 8
 //                 channels in the 128-byte swizzle the TMA store expects.
-//   warps 2, 3  : TMA stores, lane 0 of warp 2 for groups 0 and 1, lane 0 of warp 3 for groups 2 and 3, polling.
+//   warp 2      : TMA stores, lane 0 for all four groups, polling their hand-over barriers with test_wait.
 //
 // Barriers.  Every barrier has ONE producer side and ONE consumer that sees each of its phases in sequence, and every
 // ring has back-pressure, so a parity wait can neither be satisfied by the phase before last nor miss a phase (the
@@ -114,14 +115,14 @@ template <int KI, int NT>
 __device__ __forceinline__ void issue_ident_mma_sw128(uint32_t tmem_d, uint32_t ident_addr, uint32_t b_addr,
                                                       uint32_t img_bytes, uint32_t kb_bytes) {
   constexpr uint32_t idesc = make_idesc(kM, NT);
+  const uint32_t a_lo = sw128_desc_lo(ident_addr), b_lo = sw128_desc_lo(b_addr);
   uint32_t acc = 0;
 #pragma unroll
   for (int img = 0; img < 2; ++img) {
 #pragma unroll
     for (int ks = 0; ks < KI / 16; ++ks) {
-      const uint32_t a = ident_addr + (ks >> 2) * (kM * 128) + (ks & 3) * 32;
-      const uint32_t b = b_addr + img * img_bytes + (ks >> 2) * kb_bytes + (ks & 3) * 32;
-      mma_ss_f16(tmem_d, make_sw128_desc(a), make_sw128_desc(b), idesc, acc);
+      mma_ss_f16(tmem_d, sw128_desc_at(a_lo, (ks >> 2) * (kM * 128) + (ks & 3) * 32),
+                 sw128_desc_at(b_lo, img * img_bytes + (ks >> 2) * kb_bytes + (ks & 3) * 32), idesc, acc);
       acc = 1;
     }
   }
@@ -247,56 +248,77 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 #pragma unroll
       for (int l = 0; l < C::HC * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + l * 128));
     };
-    // The endpoints are read kIdxAhead tiles ahead of their use: a load issued in one iteration and consumed in the
-    // next made every iteration of this loop one DRAM round trip long -- about a tile period, so the producer could not
-    // run ahead and the epilogue groups waited for their indices 12 % of the time (profiles/r02c).
-    constexpr int kIdxAhead = 3;
+    // The endpoints are read kIdxAhead tiles ahead of their use.  The ring is indexed STATICALLY (the tile loop is
+    // unrolled by its length): a ring that is shifted by register moves makes every iteration wait for the load
+    // issued in the iteration before it -- one DRAM round trip per tile, about a tile period, so the producer never
+    // got ahead of the tensor core, the stages ran empty and the epilogue groups waited for their indices 10 % of
+    // the time (profiles/r02g: the producer warp spent 60 % of its samples on these loads and 4 % on `empty`).
+    constexpr int kIdxAhead = 4;
+    static_assert(kIdxAhead % C::NB == 0 && kIdxAhead % kE2Groups == 0, "stage / group of ring entry k are static");
     int ring[kIdxAhead][3];
 #pragma unroll
-    for (int k = 0; k < kIdxAhead; ++k)
+    for (int k = 0; k < kIdxAhead; ++k) {
+      ring[k][0] = ring[k][1] = 0;
+      ring[k][2] = -1;
       if (worker + (int64_t)k * workers < num_tiles) load_idx(worker + (int64_t)k * workers, ring[k]);
-    int i = 0;
-    for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
-      const int s = i % C::NB;
-      int cur[3];
+    }
+    const int64_t ahead = (int64_t)kIdxAhead * workers;
+    bool more = worker < num_tiles;
+    unsigned long long ptm[2] = {0, 0};   // kTiming: cycles waiting for an empty stage, tiles
+    for (int i0 = 0; more; i0 += kIdxAhead) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) cur[k] = ring[0][k];
-      prefetch_rows(cur);
-      mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkEdge2, kWrProducer, kWbEmpty), s, i);
-      if (elect_one()) {
-        uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
-        mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
+      for (int k = 0; k < kIdxAhead; ++k) {
+        const int i = i0 + k;
+        const int64_t t = worker + (int64_t)i * workers;
+        if (t >= num_tiles) { more = false; break; }
+        const int s = k % C::NB;
+        prefetch_rows(ring[k]);
+        const long long p0 = kTiming ? clock64() : 0;
+        mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkEdge2, kWrProducer, kWbEmpty), s, i);
+        if (kTiming) { ptm[0] += clock64() - p0; ptm[1] += 1; }
+        if (elect_one()) {
+          uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
+          mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < T::KBLOCKS; ++kb) {
-          if (C::MC) {   // rank 0 brings the hi halves, rank 1 the lo halves, for both CTAs
-            tma_load_2d_mc(stage + half * T::IMG_BYTES + kb * T::KB_BYTES, &map_e, half * H + kb * kKB, (int)(t * kE2NT),
-                           &full[s], (uint16_t)3);
-          } else {
-            tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s]);
-            tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s]);
+          for (int kb = 0; kb < T::KBLOCKS; ++kb) {
+            if (C::MC) {   // rank 0 brings the hi halves, rank 1 the lo halves, for both CTAs
+              tma_load_2d_mc(stage + half * T::IMG_BYTES + kb * T::KB_BYTES, &map_e, half * H + kb * kKB, (int)(t * kE2NT),
+                             &full[s], (uint16_t)3);
+            } else {
+              tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s]);
+              tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s]);
+            }
           }
         }
+        const int grp = k % kE2Groups, slot = (i / kE2Groups) % kE2IdxSlots;
+        int* ia = idx_area + (grp * kE2IdxSlots + slot) * kE2IdxInts;
+        ia[lane] = ring[k][0];
+        ia[kE2NT + lane] = ring[k][1];
+        if (lane < 2) ia[2 * kE2NT + lane] = ring[k][2];
+        mbar_arrive(&ifull[grp * kE2IdxSlots + slot]);
+        if (t + ahead < num_tiles) load_idx(t + ahead, ring[k]);
       }
-#pragma unroll
-      for (int k = 0; k + 1 < kIdxAhead; ++k) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) ring[k][j] = ring[k + 1][j];
-      }
-      if (t + (int64_t)kIdxAhead * workers < num_tiles) load_idx(t + (int64_t)kIdxAhead * workers, ring[kIdxAhead - 1]);
-      const int grp = i % kE2Groups, slot = (i / kE2Groups) % kE2IdxSlots;
-      int* ia = idx_area + (grp * kE2IdxSlots + slot) * kE2IdxInts;
-      ia[lane] = cur[0];
-      ia[kE2NT + lane] = cur[1];
-      if (lane < 2) ia[2 * kE2NT + lane] = cur[2];
-      mbar_arrive(&ifull[grp * kE2IdxSlots + slot]);
     }
-  } else if (warp == 1) {
+    if (kTiming && timing != nullptr && lane == 0) {
+      timing[((size_t)blockIdx.x * 32 + warp) * 5 + 0] = ptm[0];
+      timing[((size_t)blockIdx.x * 32 + warp) * 5 + 4] = ptm[1];
+    }
+  } else if (warp == 1 || warp == 3) {
     // ---------------------------------------------------------------- MMA issue
-    int i = 0;
-    for (int64_t t = worker; t < num_tiles; t += workers, ++i) {
+    // Two issuing warps on two schedulers, warp 1 for the even tiles of the CTA and warp 3 for the odd ones (stage
+    // and accumulator set follow the tile index, so each barrier keeps its one consumer).  One warp was busy 2.4k of
+    // the 3.2k cycles of a tile period just ISSUING (64 tcgen05.mma + their descriptors at one instruction every ~9
+    // cycles next to four epilogue warps on the same scheduler), and the accumulators of a tile arrived 1.5-3k cycles
+    // after its group had asked for them (profiles/r02h).
+    int i = warp >> 1;
+    unsigned long long mtm[4] = {0, 0, 0, 0};   // kTiming: cycles waiting for the stage, for the accumulator set, issuing; tiles
+    for (int64_t t = worker + (int64_t)i * workers; t < num_tiles; t += 2 * (int64_t)workers, i += 2) {
       const int s = i % C::NB, d = i % kE2Groups;
+      const long long m0 = kTiming ? clock64() : 0;
       mbar_wait(&full[s], (i / C::NB) & 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbFull), s, i);
+      const long long m1 = kTiming ? clock64() : 0;
       mbar_wait(&dempty[d], ((i / kE2Groups) & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrMma, kWbDEmpty), d, i);
+      const long long m2 = kTiming ? clock64() : 0;
       tc_fence_after();
       if (elect_one()) {
         const uint32_t stage = smem_u32(bufs + (size_t)s * T::BUF_BYTES);
@@ -310,15 +332,23 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         mma_commit(&dfull[d]);   // ... and the accumulators to the group
       }
       __syncwarp();
+      if (kTiming) { mtm[0] += m1 - m0; mtm[1] += m2 - m1; mtm[2] += clock64() - m2; mtm[3] += 1; }
     }
-  } else if (warp < kE2FirstEpiWarp) {
+    if (kTiming && timing != nullptr && lane == 0) {
+      timing[((size_t)blockIdx.x * 32 + warp) * 5 + 0] = mtm[0];
+      timing[((size_t)blockIdx.x * 32 + warp) * 5 + 1] = mtm[1];
+      timing[((size_t)blockIdx.x * 32 + warp) * 5 + 2] = mtm[2];
+      timing[((size_t)blockIdx.x * 32 + warp) * 5 + 4] = mtm[3];
+    }
+  } else if (warp == 2) {
     // ---------------------------------------------------------------- TMA stores
-    // Lane 0 of warp 2 stores the tiles of groups 0 and 1, lane 0 of warp 3 those of groups 2 and 3.  It POLLS its two
-    // groups without blocking on either (their tiles finish out of order).  A group cannot refill its output buffer
-    // before this thread has released it (oempty), so ofull never runs ahead of its one consumer.
+    // Lane 0 stores the tiles of all four groups.  It POLLS them with test_wait, which returns at once (try_wait would
+    // park the thread on one group's barrier for microseconds while another group's tile is ready; their tiles finish
+    // out of order).  A group cannot refill its output buffer before this thread has released it (oempty), so ofull
+    // never runs ahead of its one consumer.
     if (lane == 0) {
-      constexpr int kPer = kE2Groups / 2;
-      const int g0 = (warp - 2) * kPer;
+      constexpr int kPer = kE2Groups;
+      const int g0 = 0;
       int it[kPer];                                        // next tile iteration of each served group
 #pragma unroll
       for (int k = 0; k < kPer; ++k) it[k] = g0 + k;
@@ -336,7 +366,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         for (int k = 0; k < kPer; ++k) {
           if (!remaining(k)) continue;
           const int i = it[k], grp = g0 + k;
-          if (!mbar_test(&ofull[grp], (i / kE2Groups) & 1)) continue;
+          if (!mbar_poll(&ofull[grp], (i / kE2Groups) & 1)) continue;
           const int64_t t = worker + (int64_t)i * workers;
           const uint8_t* ob = obufs + (size_t)grp * C::OBUF_BYTES;
 #pragma unroll
@@ -355,7 +385,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         if (progressed) {
           guard = SpinGuard();
         } else {
-          __nanosleep(32);
+          __nanosleep(64);
           guard.poll(watch, watch_tag(kWkEdge2, kWrStore, kWbOFull), (uint32_t)g0, (uint32_t)((it[0] / kE2Groups) & 1), it[0]);
         }
       }
@@ -408,93 +438,93 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       int cur = -1;
       float num = 0.f, den = 0.f;
 
-      // Software pipeline over four batches of eight edges: the gathers of batch b+1 -- xa = (B1h', A2h)[src] and
-      // xb = B2h'[dst], one coalesced row segment per warp each -- are in flight while batch b is computed.
-      constexpr int kEB = 8;
+      // Software pipeline over the tile's eight quads of edges with three quads of gathers in flight: xa = (B1h', A2h)[src]
+      // (one coalesced 8-byte row segment per warp and edge) and xb = B2h'[dst] of quad k + 3 are requested before quad
+      // k is computed, into four statically indexed register buffers (the q0 loop is unrolled by the ring length).
+      // With two batches of eight (r02c) a gather had one batch of arithmetic to arrive in and 10 % of all warp
+      // samples sat on its first use (profiles/r02g).
+      constexpr int kQ = 4, kNQ = kE2Chunk / kQ, kRing = 4;
       const int* ia_src = ia;                            // endpoints of the chunk's 32 edges: warp-uniform reads
       const int* ia_dst = ia + kE2NT;
-      auto fetch = [&](int b, float2 (&xa)[kEB], float (&xb)[kEB]) {
-        int sj[kEB], dj[kEB];
-        *reinterpret_cast<int4*>(&sj[0]) = *reinterpret_cast<const int4*>(ia_src + b * kEB);
-        *reinterpret_cast<int4*>(&sj[4]) = *reinterpret_cast<const int4*>(ia_src + b * kEB + 4);
-        *reinterpret_cast<int4*>(&dj[0]) = *reinterpret_cast<const int4*>(ia_dst + b * kEB);
-        *reinterpret_cast<int4*>(&dj[4]) = *reinterpret_cast<const int4*>(ia_dst + b * kEB + 4);
+      auto fetch = [&](int qd, float2 (&xa)[kQ], float (&xb)[kQ]) {
+        int sj[kQ], dj[kQ];
+        *reinterpret_cast<int4*>(&sj[0]) = *reinterpret_cast<const int4*>(ia_src + qd * kQ);
+        *reinterpret_cast<int4*>(&dj[0]) = *reinterpret_cast<const int4*>(ia_dst + qd * kQ);
 #pragma unroll
-        for (int u = 0; u < kEB; ++u) xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj[u] * ldPb));
-        // B2h'[dst]: the four edges of a quad share it unless a destination segment opens at its 2nd..4th edge
-        const unsigned m8 = segmask >> (b * kEB);
+        for (int u = 0; u < kQ; ++u) xa[u] = __ldg(reinterpret_cast<const float2*>(Pc + (int64_t)sj[u] * ldPb));
+        // B2h'[dst]: the four edges of a quad share it unless a destination segment opens at its 2nd..4th edge.  The
+        // shared value stays in xb[0] and compute() selects it: copying it into xb[1..3] here would make this warp
+        // wait for the load inside the fetch, i.e. before the arithmetic that is meant to cover its latency.
+        xb[0] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj[0] * ldPb));
+        if ((segmask >> (qd * kQ)) & 0xeu) {   // warp-uniform
 #pragma unroll
-        for (int hq = 0; hq < kEB; hq += 4) {
-          if (((m8 >> hq) & 0xeu) == 0) {   // warp-uniform
-            const float v = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj[hq] * ldPb));
-            xb[hq] = v; xb[hq + 1] = v; xb[hq + 2] = v; xb[hq + 3] = v;
-          } else {
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-              xb[hq + w] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj[hq + w] * ldPb));
-          }
+          for (int w = 1; w < kQ; ++w) xb[w] = __ldg(reinterpret_cast<const float*>(Pb2 + (int64_t)dj[w] * ldPb));
         }
       };
-      auto compute = [&](auto full_tag, int b, const float2 (&xa)[kEB], const float (&xb)[kEB]) {
+      auto compute = [&](auto full_tag, int qd, const float2 (&xa)[kQ], const float (&xb)[kQ]) {
         constexpr bool kFullChunk = decltype(full_tag)::value;   // all 32 edges exist: no per-edge validity tests
+        uint32_t zr[4], er[4] = {0u, 0u, 0u, 0u};
+        tmem_ld4(taddr + qd * kQ, zr);
+        if (kResidual) tmem_ld4(taddr + kE2NT + qd * kQ, er);   // e / 16 = hi + lo, exact
+        tmem_ld_wait();
+        const unsigned mb = (segmask >> (qd * kQ)) & 0xfu;
+        const bool shared_b2 = (mb & 0xeu) == 0;                 // warp-uniform
+        float v[4], sg[4];
 #pragma unroll
-        for (int hb = 0; hb < kEB; hb += 4) {
-          uint32_t zr[4], er[4] = {0u, 0u, 0u, 0u};
-          tmem_ld4(taddr + b * kEB + hb, zr);
-          if (kResidual) tmem_ld4(taddr + kE2NT + b * kEB + hb, er);   // e / 16 = hi + lo, exact
-          tmem_ld_wait();
-          float v[4], sg[4];
+        for (int w = 0; w < 4; ++w) {
+          const float b2 = (w == 0 || shared_b2) ? xb[0] : xb[w];
+          // scaled domain: v = e' / 16 (the norm affine is folded into D, B1h' and B2h' by the caller)
+          v[w] = fmaf(fmaxf(__uint_as_float(zr[w]) + xa[w].x + b2, 0.f), kXScale, __uint_as_float(er[w]));
+          sg[w] = (kFullChunk || qd * kQ + w < n) ? sigmoid16f_fast(v[w]) : 0.f;
+        }
+        tmem_st4(taddr + kE2NT + qd * kQ, v);   // e' / 16 over the residual it was computed from (same lane)
+        if (mb == 0) {                 // warp-uniform: the four edges continue the running segment
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const int u = hb + w;
-            // scaled domain: v = e' / 16 (the norm affine is folded into D, B1h' and B2h' by the caller)
-            v[w] = fmaf(fmaxf(__uint_as_float(zr[w]) + xa[u].x + xb[u], 0.f), kXScale, __uint_as_float(er[w]));
-            sg[w] = (kFullChunk || b * kEB + u < n) ? sigmoid16f_fast(v[w]) : 0.f;
+            num = fmaf(sg[w], xa[w].y, num);
+            den += sg[w];
           }
-          tmem_st4(taddr + kE2NT + b * kEB + hb, v);   // e' / 16 over the residual it was computed from (same lane)
-          const unsigned mb = (segmask >> (b * kEB + hb)) & 0xfu;
-          if (mb == 0) {                 // warp-uniform: the four edges continue the running segment
+        } else {
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              num = fmaf(sg[w], xa[hb + w].y, num);
-              den += sg[w];
-            }
-          } else {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              if (mb & (1u << w)) {      // warp-uniform: close the running segment, open the next
-                if (cur >= 0) {
-                  if (cur == head_dst) {
-                    carry[(chunk * 4 + 0) * H + c] = num;
-                    carry[(chunk * 4 + 1) * H + c] = den;
-                  } else {
-                    F[(int64_t)cur * H + c] = gate_div(num, den);
-                  }
+          for (int w = 0; w < 4; ++w) {
+            if (mb & (1u << w)) {      // warp-uniform: close the running segment, open the next
+              if (cur >= 0) {
+                if (cur == head_dst) {
+                  carry[(chunk * 4 + 0) * H + c] = num;
+                  carry[(chunk * 4 + 1) * H + c] = den;
+                } else {
+                  F[(int64_t)cur * H + c] = gate_div(num, den);
                 }
-                cur = ia_dst[b * kEB + hb + w];
-                num = 0.f;
-                den = 0.f;
               }
-              num = fmaf(sg[w], xa[hb + w].y, num);
-              den += sg[w];
+              cur = ia_dst[qd * kQ + w];
+              num = 0.f;
+              den = 0.f;
             }
+            num = fmaf(sg[w], xa[w].y, num);
+            den += sg[w];
           }
         }
       };
-      float2 fa0[kEB], fa1[kEB];
-      float fb0[kEB], fb1[kEB];
-      fetch(0, fa0, fb0);                                // in flight while the tile's products complete
+      float2 fa[kRing][kQ];
+      float fb[kRing][kQ];
+#pragma unroll
+      for (int k = 0; k < kRing; ++k)
+#pragma unroll
+        for (int w = 0; w < kQ; ++w) fb[k][w] = 0.f;   // xb[1..3] of a quad with one destination are never loaded
+#pragma unroll
+      for (int k = 0; k + 1 < kRing; ++k) fetch(k, fa[k], fb[k]);   // in flight while the tile's products complete
       const long long t2 = kTiming ? clock64() : 0;
       mbar_wait(&dfull[grp], jj & 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbDFull), grp, i);
       tc_fence_after();
       const long long t3 = kTiming ? clock64() : 0;
       auto run_chunk = [&](auto full_tag) {
 #pragma unroll 1
-        for (int b = 0; b < kE2Chunk / kEB; b += 2) {
-          fetch(b + 1, fa1, fb1);
-          compute(full_tag, b, fa0, fb0);
-          if (b + 2 < kE2Chunk / kEB) fetch(b + 2, fa0, fb0);
-          compute(full_tag, b + 1, fa1, fb1);
+        for (int q0 = 0; q0 < kNQ; q0 += kRing) {
+#pragma unroll
+          for (int k = 0; k < kRing; ++k) {
+            if (q0 + k + kRing - 1 < kNQ) fetch(q0 + k + kRing - 1, fa[(k + kRing - 1) % kRing], fb[(k + kRing - 1) % kRing]);
+            compute(full_tag, q0 + k, fa[k], fb[k]);
+          }
         }
       };
       if (n == kE2Chunk) run_chunk(std::true_type{});
@@ -513,24 +543,26 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       // e' (fp32, scaled) sits in this warp's 32 TMEM lanes x 32 columns: read it back as fragments, split, and store
       // transposed into the group's output buffer: edge row T, channels 16 hl + 8 a + [0, 8) = one 16-byte swizzle chunk.
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      // Both 16-lane halves are read before anything else happens, and that is the LAST read of this accumulator
+      // set: it goes back to the MMA warp here, so that the products of the group's next tile (about 1.1k cycles the
+      // group cannot hide: tensor memory holds one set per group) run under the conversion and the hand-off below.
+      uint32_t fr[2][16];
+      tmem_ld_frag16x32(taddr + kE2NT, fr[0]);
+      tmem_ld_frag16x32(taddr + kE2NT + ((uint32_t)16 << 16), fr[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dempty[grp]);
       // the buffer still holds the group's previous tile until the store thread has handed it back
       mbar_wait(&oempty[grp], (jj & 1) ^ 1, 32, watch, watch_tag(kWkEdge2, kWrEpilogue, kWbOEmpty), grp, i);
 #pragma unroll
       for (int hl = 0; hl < 2; ++hl) {
-        uint32_t fr[16];
-        tmem_ld_frag16x32(taddr + kE2NT + ((uint32_t)(hl * 16) << 16), fr);
-        tmem_ld_wait();
-        if (hl == 1) {   // last read of this accumulator set: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&dempty[grp]);
-        }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           uint32_t fh[4], fl[4];
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {   // edge block cb: edges 8 cb + 2 (T % 4), + 1 of channel T / 4 + 8 a
-            const float x0 = __uint_as_float(fr[4 * cb + 2 * a]), x1 = __uint_as_float(fr[4 * cb + 2 * a + 1]);
+            const float x0 = __uint_as_float(fr[hl][4 * cb + 2 * a]), x1 = __uint_as_float(fr[hl][4 * cb + 2 * a + 1]);
             const __half2 hh = __floats2half2_rn(x0, x1);
             const float2 back = __half22float2(hh);
             const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);

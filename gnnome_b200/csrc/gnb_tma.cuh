@@ -114,21 +114,33 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
   return (uint32_t)(kb * (NT * 128) + r * 128 + ((((kk >> 3) ^ (r & 7)) << 4) | ((kk & 7) << 1)));
 }
 
+// The low word of that descriptor (start address field + LBO = 1) and the descriptor of an operand `byte_off` bytes
+// further into the same stage: the address field is (addr >> 4) mod 2^14 and a stage never crosses the 256 KB the
+// field spans, so advancing it is ONE 32-bit add.  The MMA-issuing thread computes the base once per tile; building
+// every descriptor from its byte address cost five uniform-datapath instructions per tcgen05.mma, and that thread --
+// one warp sharing a scheduler with four epilogue warps -- was busy 60-70 % of the time in the aggregation kernel,
+// so that the accumulators of a tile arrived ~3k cycles after its epilogue group had asked for them (profiles/r02h).
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t sw128_desc_at(uint32_t base_lo, uint32_t byte_off) {
+  constexpr uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+  return ((uint64_t)hi << 32) | (uint64_t)(base_lo + (byte_off >> 4));
+}
+
 // The three split-precision products of one tile: D (+)= Whi*Xhi + Whi*Xlo + Wlo*Xhi (small terms first).
 // tmem_w: first column of the W_hi image (W_lo at + K/2); b_addr: shared address of the stage.
 template <int K, int NT>
 __device__ __forceinline__ void issue_tile_mma_sw128(uint32_t tmem_w, uint32_t tmem_d, uint32_t b_addr) {
   using T = Tile2<K, NT>;
   constexpr uint32_t idesc = make_idesc(kM, NT);
+  const uint32_t lo0 = sw128_desc_lo(b_addr);
   uint32_t acc = 0;
 #pragma unroll
   for (int term = 0; term < 3; ++term) {  // Wlo*Xhi, Whi*Xlo, Whi*Xhi
     const uint32_t a0 = tmem_w + (term == 0 ? T::W_COLS : 0);
-    const uint32_t b0 = b_addr + (term == 1 ? T::IMG_BYTES : 0);
 #pragma unroll
     for (int ks = 0; ks < T::KSTEPS; ++ks) {
-      const uint32_t baddr = b0 + (ks >> 2) * T::KB_BYTES + (ks & 3) * 32;
-      mma_ts_f16(tmem_d, a0 + ks * 8, make_sw128_desc(baddr), idesc, acc);
+      const uint32_t off = (term == 1 ? T::IMG_BYTES : 0) + (ks >> 2) * T::KB_BYTES + (ks & 3) * 32;
+      mma_ts_f16(tmem_d, a0 + ks * 8, sw128_desc_at(lo0, off), idesc, acc);
       acc = 1;
     }
   }

@@ -33,6 +33,8 @@ with torch.no_grad():
     lib.gnb_debug_edge_timing(None)
 ms = ev0.elapsed_time(ev1)
 b = buf.cpu().double()
+role = b[:, :4, :].clone()   # warp 0: producer [empty wait, -, -, -, tiles]; warp 1: MMA issue [full wait, dempty wait, issue, -, tiles]
+b[:, :4, :] = 0
 live = b[:, :, 4] > 0
 tiles = b[:, :, 4][live]
 print(f'H={H} E={m}: kernel {ms:.2f} ms; epilogue warps with work: {int(live.sum())}; tiles per warp {tiles.mean():.1f}')
@@ -44,3 +46,9 @@ for k in range(4):
 print(f'  total {sum((b[:, :, k][live] / tiles).mean() for k in range(4)):.0f} cycles per tile per warp; kernel cycles/tile-visit at 1.9 GHz: {ms * 1e-3 * 1.9e9 / tiles.mean():.0f}')
 for w in (4, 5, 8, 12, 16):
     print(f'  CTA 0 warp {w}:', [int(v) for v in (b[0, w, :4] / max(b[0, w, 4], 1)).tolist()], 'tiles', int(b[0, w, 4]))
+pt, mt = role[:, 0, 4].clamp(min=1), role[:, 1, 4].clamp(min=1)
+print(f'  producer warp: {(role[:, 0, 0] / pt).mean():.0f} cycles / tile waiting for an empty stage ({pt.mean():.0f} tiles per CTA)')
+for w in (1, 3):
+    mt = role[:, w, 4].clamp(min=1)
+    print(f'  MMA warp {w}: per tile {(role[:, w, 0] / mt).mean():.0f} cycles waiting for the stage (TMA), {(role[:, w, 1] / mt).mean():.0f} for the accumulator set, '
+          f'{(role[:, w, 2] / mt).mean():.0f} issuing ({mt.mean():.0f} tiles)')

@@ -4,6 +4,8 @@
 #   smoke            __graft_entry__.smoke()
 #   tests[:EXPR]     pytest -m gpu (optionally -k EXPR)
 #   bench[:WL]       bench.py --workload WL (default cfg3) -> gpurun_out/bench_WL.json + a one-line summary
+#   benchq[:WL]      the same without the CPU legs (kernel work only; -> gpurun_out/benchq_WL.json)
+#   edgetime[:H]     tools/edge_timing.py: cycle accounting of the aggregation kernel's epilogue warps
 #   ref              bench.py --impl reference
 #   stress[:WL:N:P]  P fresh processes x N forwards of workload WL (tools/stress.py), default cfg3:100:3
 #   dist:N[:WL]      tools/dist_check.py (inference + training equivalence) + bench.py --workload WL (default cfg3) under torchrun on N GPUs
@@ -36,6 +38,11 @@ for st in "${steps[@]}"; do
            grep -E "^(FAILED|ERROR)|passed|failed|rc=" gpurun_out/pytest_gpu.log | tail -8 ;;
     bench) wl=${a1:-cfg3}; timeout 900 python bench.py --workload "$wl" --steps 5 --warmup 3 > "gpurun_out/bench_$wl.json" 2> "gpurun_out/bench_$wl.err"
            echo "bench $wl rc=$?"; summ "gpurun_out/bench_$wl.json" ;;
+    benchq) wl=${a1:-cfg3}; timeout 600 python bench.py --workload "$wl" --steps 5 --warmup 3 --no-cpu > "gpurun_out/benchq_$wl.json" 2> "gpurun_out/benchq_$wl.err"
+           echo "benchq $wl rc=$?"; summ "gpurun_out/benchq_$wl.json" ;;
+    edgetime) timeout 300 python tools/edge_timing.py ${a1:-256} > "gpurun_out/edge_timing_${a1:-256}.txt" 2>&1; grep -v "CTA 0" "gpurun_out/edge_timing_${a1:-256}.txt" | tail -9 ;;
+    power) timeout 600 python tools/power_probe.py ${a1:-cfg3} ${a2:-3} > "gpurun_out/power_${a1:-cfg3}.txt" 2>&1; tail -5 "gpurun_out/power_${a1:-cfg3}.txt" ;;
+    trywait) timeout 120 tools/microbench/trywait_probe > gpurun_out/trywait_probe.txt 2>&1; cat gpurun_out/trywait_probe.txt ;;
     ref)   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.json ;;
     stress) wl=${a1:-cfg3}; n=${a2:-100}; p=${a3:-3}
            for i in $(seq 1 "$p"); do timeout 900 python tools/stress.py "$wl" "$n" > /dev/null 2> "gpurun_out/stress_$i.err"; echo "stress $wl x$n process $i rc=$? $(grep -c ' ok ' gpurun_out/stress_$i.err) forwards ok; $(tail -1 gpurun_out/stress_$i.err)"; done ;;
