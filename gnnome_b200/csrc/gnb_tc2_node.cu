@@ -196,16 +196,21 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
   const unsigned gmask = TPN >= 32 ? 0xffffffffu : (((1u << TPN) - 1u) << (((threadIdx.x & 31) / TPN) * TPN));
   const int64_t stride = (int64_t)gridDim.x * NPB;
   int64_t i = node_begin + (int64_t)blockIdx.x * NPB + slot;
-  int qa = 0, qb = 0, pa = 0, pb = 0;
+  int qa = 0, qb = 0, pa = 0, pb = 0, xa = 0, xb = 0;
   if (i < node_end) {
     if (agg) { qa = g.out_ptr[i]; qb = g.out_ptr[i + 1]; }
     if (!partial_out) { pa = g.in_ptr[i]; pb = g.in_ptr[i + 1]; }
+    if (xp_ptr) { xa = xp_ptr[i]; xb = xp_ptr[i + 1]; }
   }
   for (; i < node_end; i += stride) {
-    int nqa = 0, nqb = 0, npa = 0, npb = 0;   // CSR pointers of this group's next node: one iteration ahead
+    int nqa = 0, nqb = 0, npa = 0, npb = 0, nxa = 0, nxb = 0;   // CSR pointers of this group's next node: one iteration ahead
     if (i + stride < node_end) {
       if (agg) { nqa = g.out_ptr[i + stride]; nqb = g.out_ptr[i + stride + 1]; }
       if (!partial_out) { npa = g.in_ptr[i + stride]; npb = g.in_ptr[i + stride + 1]; }
+      // the list of partial sums other ranks computed for the node (multi-GPU): read here, not after the edge loop,
+      // where the two dependent loads added a DRAM round trip to every node of a latency-bound kernel (the sharded
+      // launches ran 30 % longer per node than the single-GPU ones, profiles/r02f)
+      if (xp_ptr) { nxa = xp_ptr[i + stride]; nxb = xp_ptr[i + stride + 1]; }
     }
     // ---- everything that depends on the node id only ------------------------------------------------
     F8 a1 = f8_zero(), hin = f8_zero(), f = f8_zero();
@@ -259,7 +264,7 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
         continue;
       }
       if (xp_ptr) {       // multi-GPU: partial sums other ranks computed for this node, in rank order
-        for (int r = xp_ptr[i], re = xp_ptr[i + 1]; r < re; ++r) {
+        for (int r = xa; r < xb; ++r) {
           const float* row = xp_buf + (int64_t)xp_row[r] * 2 * H;
           const F8 xn = f8_load(row + c0), xd = f8_load(row + H + c0);
 #pragma unroll
@@ -300,10 +305,10 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       for (int k = 0; k < 8; ++k) xs[k] = u.v[k] * kXScale;
       uint4 hh, ll;
       split8(xs, hh, ll);
-      *reinterpret_cast<uint4*>(h16_out + (i - node_begin) * 2 * H + c0) = hh;
-      *reinterpret_cast<uint4*>(h16_out + (i - node_begin) * 2 * H + H + c0) = ll;
+      *reinterpret_cast<uint4*>(h16_out + i * 2 * H + c0) = hh;     // absolute rows, like h_out
+      *reinterpret_cast<uint4*>(h16_out + i * 2 * H + H + c0) = ll;
     }
-    qa = nqa; qb = nqb; pa = npa; pb = npb;
+    qa = nqa; qb = nqb; pa = npa; pb = npb; xa = nxa; xb = nxb;
   }
 }
 

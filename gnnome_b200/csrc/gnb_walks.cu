@@ -7,6 +7,7 @@
 // worker thread, and the candidates of one iteration run on a pool of threads (they only read the shared visited map).
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -14,6 +15,33 @@
 
 namespace gnb {
 namespace {
+
+// Visited maps are N bytes each and get_contigs_greedy calls the walker once per contig: allocating and zero-filling
+// one per worker thread and call would cost ~1 GB of memset per decoder iteration on a 10M-node graph.  A worker
+// borrows a map from this pool and returns it all-zero (it clears what it touched), so a map is zero-filled once.
+class MarkPool {
+ public:
+  std::vector<uint8_t> take(size_t n) {
+    std::vector<uint8_t> m;
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      if (!free_.empty()) {
+        m = std::move(free_.back());
+        free_.pop_back();
+      }
+    }
+    if (m.size() < n) m.assign(n, 0);   // a map of another (smaller) graph: start over
+    return m;
+  }
+  void give(std::vector<uint8_t>&& m) {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (free_.size() < 64) free_.push_back(std::move(m));
+  }
+ private:
+  std::mutex mu_;
+  std::vector<std::vector<uint8_t>> free_;
+};
+static MarkPool g_marks;
 
 struct Walker {
   const gnb_walk_graph_t& g;
@@ -23,7 +51,13 @@ struct Walker {
   std::vector<int32_t> touched;
 
   Walker(const gnb_walk_graph_t& graph, const float* lp, const uint8_t* vo)
-      : g(graph), logp(lp), visited_old(vo), mark((size_t)graph.num_nodes, 0) {}
+      : g(graph), logp(lp), visited_old(vo), mark(g_marks.take((size_t)graph.num_nodes)) {}
+  ~Walker() {
+    reset();
+    g_marks.give(std::move(mark));
+  }
+  Walker(const Walker&) = delete;
+  Walker& operator=(const Walker&) = delete;
 
   void set(int32_t v) {
     if (!mark[v]) {
@@ -123,6 +157,7 @@ extern "C" int gnb_greedy_walks(const gnb_walk_graph_t* g, const float* log_prob
                 "gnb_greedy_walks: candidate %lld has an endpoint out of range", (long long)k);
   std::vector<Candidate> res((size_t)n_cand);
   int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (threads <= 0 && T > 16) T = 16;   // the walks are short: more threads only add start-up cost
   if (T < 1) T = 1;
   if ((int64_t)T > n_cand) T = (int)n_cand;
   auto work = [&](int t) {

@@ -216,9 +216,9 @@ void gnb_debug_edge_timing(void* buf);
  * launch failure with a record (run it in a throw-away process: the CUDA context does not survive the trap). */
 void gnb_debug_store_delay_ns(int ns);
 
-/* gnb_node_update with e' read from split16 images; writes h' as fp32 rows (h_out, row i) and, if h16_out is
- * not NULL, as split16 images of the rows node_begin .. node_end (row i - node_begin) for the next layer's
- * gnb_node_linear_tc2 (gated_gcn_full.py:117-137). */
+/* gnb_node_update with e' read from split16 images; writes h' of the nodes node_begin .. node_end as fp32 rows
+ * (h_out, row i) and, if h16_out is not NULL, as split16 images (h16_out, row i as well: both outputs are indexed
+ * by the absolute node id) for the next layer's gnb_node_linear_tc2 (gated_gcn_full.py:117-137). */
 int gnb_node_update2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* e16,
                      const float* F, const float* carry, const float* h_in, const float* scale_h,
                      const float* shift_h, float* h_out, void* h16_out, int flags, int chunk,
