@@ -194,24 +194,32 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
   const bool agg = sym || partial_out;
   const int a1_off = sym ? 4 * H : 3 * H;
   const unsigned gmask = TPN >= 32 ? 0xffffffffu : (((1u << TPN) - 1u) << (((threadIdx.x & 31) / TPN) * TPN));
-  const int64_t stride = (int64_t)gridDim.x * NPB;
-  int64_t i = node_begin + (int64_t)blockIdx.x * NPB + slot;
-  int qa = 0, qb = 0, pa = 0, pb = 0, xa = 0, xb = 0;
-  if (i < node_end) {
-    if (agg) { qa = g.out_ptr[i]; qb = g.out_ptr[i + 1]; }
-    if (!partial_out) { pa = g.in_ptr[i]; pb = g.in_ptr[i + 1]; }
-    if (xp_ptr) { xa = xp_ptr[i]; xb = xp_ptr[i + 1]; }
+  // Node ids and counts fit 32 bits (the graph's indices are int32); the loop state is kept narrow because this kernel
+  // sits at its register cap.
+  const int stride = (int)gridDim.x * NPB;
+  const int count = (int)(node_end - node_begin);
+  auto node_at = [&](int k) -> int { return (int)node_begin + k; };
+  int k = (int)blockIdx.x * NPB + slot;
+  int i32 = k < count ? node_at(k) : 0;
+  int qa = 0, qb = 0, pa = 0, pb = 0;
+  if (k < count) {
+    if (agg) { qa = g.out_ptr[i32]; qb = g.out_ptr[i32 + 1]; }
+    if (!partial_out) { pa = g.in_ptr[i32]; pb = g.in_ptr[i32 + 1]; }
   }
-  for (; i < node_end; i += stride) {
-    int nqa = 0, nqb = 0, npa = 0, npb = 0, nxa = 0, nxb = 0;   // CSR pointers of this group's next node: one iteration ahead
-    if (i + stride < node_end) {
-      if (agg) { nqa = g.out_ptr[i + stride]; nqb = g.out_ptr[i + stride + 1]; }
-      if (!partial_out) { npa = g.in_ptr[i + stride]; npb = g.in_ptr[i + stride + 1]; }
-      // the list of partial sums other ranks computed for the node (multi-GPU): read here, not after the edge loop,
-      // where the two dependent loads added a DRAM round trip to every node of a latency-bound kernel (the sharded
-      // launches ran 30 % longer per node than the single-GPU ones, profiles/r02f)
-      if (xp_ptr) { nxa = xp_ptr[i + stride]; nxb = xp_ptr[i + stride + 1]; }
+  for (; k < count; k += stride) {
+    const int64_t i = i32;
+    int nqa = 0, nqb = 0, npa = 0, npb = 0;   // CSR pointers of this group's next node: one iteration ahead
+    int inext = 0;
+    if (k + stride < count) {
+      inext = node_at(k + stride);
+      if (agg) { nqa = g.out_ptr[inext]; nqb = g.out_ptr[inext + 1]; }
+      if (!partial_out) { npa = g.in_ptr[inext]; npb = g.in_ptr[inext + 1]; }
     }
+    // the list of partial sums other ranks computed for the node (multi-GPU): requested here, ahead of the edge
+    // loop -- read after it, the two dependent loads added a DRAM round trip to every node of a latency-bound
+    // kernel (the sharded launches ran 30 % longer per node than the single-GPU ones, profiles/r02f)
+    int xa = 0, xb = 0;
+    if (xp_ptr) { xa = xp_ptr[i]; xb = xp_ptr[i + 1]; }
     // ---- everything that depends on the node id only ------------------------------------------------
     F8 a1 = f8_zero(), hin = f8_zero(), f = f8_zero();
     const bool f_direct = pb > pa && pa / chunk == (pb - 1) / chunk;   // the whole in-segment sits in one chunk
@@ -260,7 +268,7 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       if (partial_out) {  // multi-GPU: un-normalised partial sums of a halo source node, for its owner
         f8_store(partial_out + (i - node_begin) * 2 * H + c0, num);
         f8_store(partial_out + (i - node_begin) * 2 * H + H + c0, den);
-        qa = nqa; qb = nqb;
+        qa = nqa; qb = nqb; i32 = inext;
         continue;
       }
       if (xp_ptr) {       // multi-GPU: partial sums other ranks computed for this node, in rank order
@@ -308,7 +316,7 @@ node_update2_kernel(gnb_graph_t g, const float* __restrict__ P, int64_t ldP, con
       *reinterpret_cast<uint4*>(h16_out + i * 2 * H + c0) = hh;     // absolute rows, like h_out
       *reinterpret_cast<uint4*>(h16_out + i * 2 * H + H + c0) = ll;
     }
-    qa = nqa; qb = nqb; pa = npa; pb = npb; xa = nxa; xb = nxb;
+    qa = nqa; qb = nqb; pa = npa; pb = npb; i32 = inext;
   }
 }
 

@@ -20,6 +20,8 @@ The arithmetic is delegated to a ``kernels`` object (``CudaKernels``: the C-ABI 
 ``gnnome_b200.ops``); the CPU ``gloo`` tests plug a torch emulation of the same per-op contracts in
 to check the partition / halo logic without a GPU.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -80,8 +82,19 @@ class DistComm:
     def all_to_all(self, out, inp, out_splits=None, in_splits=None):
         dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.group)
 
+    def all_to_all_start(self, out, inp, out_splits=None, in_splits=None):
+        """The same exchange started asynchronously: the collective runs on the backend's own stream behind the work
+        already queued on the current one; ``.wait()`` on the returned handle orders the current stream behind it."""
+        return dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                      group=self.group, async_op=True)
+
     def all_reduce_max(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
+
+class _Done:
+    def wait(self):
+        return True
 
 
 class HaloPlan:
@@ -127,6 +140,15 @@ class HaloPlan:
         if self.world > 1:
             self.comm.all_to_all(recv, rows_out, self.recv_counts, self.send_counts)
         return recv
+
+    def to_consumers_start(self, rows_out, recv):
+        """``to_consumers`` without waiting: returns a handle whose ``wait()`` must be called before ``recv`` is read."""
+        if self.world > 1:
+            start = getattr(self.comm, 'all_to_all_start', None)
+            if start is not None:
+                return start(recv, rows_out, self.recv_counts, self.send_counts)
+            self.comm.all_to_all(recv, rows_out, self.recv_counts, self.send_counts)
+        return _Done()
 
     def to_owners(self, rows_out, recv):
         """consumer -> owner: ``rows_out`` [n_halo][W] -> ``recv`` [n_send][W] (send_idx order)."""
@@ -185,6 +207,24 @@ class CudaKernels:
 
     def gather_rows(self, table, idx, out=None):
         return self.ops.gather_rows(table, idx, out=out)
+
+    def project_rows(self, pk, h, idx, M, out):
+        """The first ``M`` columns of the layer's node projection for the rows ``idx`` only (the halo rows a peer is
+        waiting for), bit-identical to the same rows of ``node_linear_layer``: a row's products do not depend on the
+        tile it is computed in.  Split16 state only (None otherwise: the caller falls back to gathering from P)."""
+        if not isinstance(h, tuple):
+            return None
+        h16 = h[1]                                                   # [rows][2][K] fp16 == [rows][K] 4-byte words
+        rows16 = self.ops.gather_rows(h16.view(h16.shape[0], -1).view(torch.float32), idx,
+                                      out=self._scratch('h16_send', (idx.numel(), h16.shape[2])))
+        return self.ops.node_linear_tc2(rows16.view(torch.float16).view(idx.numel(), 2, h16.shape[2]), pk['Wn_t'], pk['bn'],
+                                        M, out=out)
+
+    def _scratch(self, name, shape):
+        t = self.spare.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self.spare[name] = torch.empty(shape, dtype=torch.float32, device=self.device)
+        return t
 
     def edge_forward(self, gi, H, P, pk, e_pos, F, carry, flags):
         if e_pos.dtype == torch.float16:
@@ -266,6 +306,8 @@ class ShardedForward:
         del src, dst
         self._host = None
         self.ws = {}
+        # project + send the halo rows ahead of the full projection (False / GNB_OVERLAP=0: the serial schedule)
+        self.overlap = os.environ.get('GNB_OVERLAP', '1') != '0'
 
     def local_sizes(self):
         return self.shard.n_local, self.shard.num_edges
@@ -294,14 +336,30 @@ class ShardedForward:
             pk = k.layer_pack(conv)
             flags = conv._flags()
             carry = self._buf('carry', k.carry_shape(gi, H))
-            k.node_linear_layer(pk, h, nb * H, P[:n_own])
-            if plan.active:                                        # exchange (1)
-                out_rows = k.gather_rows(P[:n_own, :2 * H], plan.send_idx, self._buf('s1', (plan.n_send, 2 * H)))
-                halo = plan.to_consumers(out_rows, self._buf('r1', (n_halo, 2 * H)))
-                P[n_own:, :2 * H].copy_(halo)
+            # exchange (1).  The (B1h', A2h) rows the peers are waiting for are projected FIRST, from the few h rows
+            # they come from, and travel while the whole table is projected (the exchange used to sit between the
+            # projection and the edge pass: ~0.9 ms per layer of an 8-GPU step with nothing to hide it behind).
+            early = None
+            if plan.active and self.overlap and hasattr(k, 'project_rows'):
+                early = k.project_rows(pk, h, plan.send_idx, 2 * H, self._buf('s1', (plan.n_send, 2 * H)))
+            if early is not None:
+                pending = plan.to_consumers_start(early, self._buf('r1', (n_halo, 2 * H)))
+                k.node_linear_layer(pk, h, nb * H, P[:n_own])
+                pending.wait()
+                P[n_own:, :2 * H].copy_(self.ws['r1'])
+            else:
+                k.node_linear_layer(pk, h, nb * H, P[:n_own])
+                if plan.active:
+                    out_rows = k.gather_rows(P[:n_own, :2 * H], plan.send_idx, self._buf('s1', (plan.n_send, 2 * H)))
+                    halo = plan.to_consumers(out_rows, self._buf('r1', (n_halo, 2 * H)))
+                    P[n_own:, :2 * H].copy_(halo)
             k.edge_forward(gi, H, P, pk, e_pos, Fb, carry, flags)
+            # exchange (2) stays between the two kernels it connects.  Hiding it was tried (all owned nodes updated
+            # without the remote sums while they travel, the nodes that receive some computed again from a node list):
+            # bit-identical, but the second pass over those scattered nodes costs more than the exchange it hides
+            # (5.7 ms against ~1 ms per layer at 2 GPUs on the bench graph, profiles/r02h).
             xp_buf = None
-            if self.sym and plan.active:                         # exchange (2)
+            if self.sym and plan.active:
                 part = self._buf('s2', (n_halo, 2 * H))
                 k.reverse_partial(gi, H, P, e_pos, n_own, n_local, part)
                 xp_buf = plan.to_owners(part, self._buf('r2', (plan.n_send, 2 * H)))

@@ -58,6 +58,15 @@ class EmulKernels:
             out[:, 3 * H:4 * H] = lin(conv.A_1)
         return out
 
+    def project_rows(self, conv, h, idx, M, out):
+        H = h.shape[1]
+        assert M == 2 * H
+        hs = h[idx.long()]
+        lin = lambda m: F.linear(hs, m.weight.detach().to(self.dtype), m.bias.detach().to(self.dtype))
+        out[:, 0:2 * H:2] = lin(conv.B_1)
+        out[:, 1:2 * H:2] = lin(conv.A_2)
+        return out
+
     def gather_rows(self, table, idx, out=None):
         res = table[idx.long()]
         if out is not None:
