@@ -60,6 +60,7 @@ SIGNATURES = {
     'gnb_edge_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _I, _P]),
     'gnb_debug_edge_timing': (None, [_P]),
     'gnb_debug_store_delay_ns': (None, [_I]),
+    'gnb_debug_edge_mode': (None, [_I]),
     'gnb_node_update2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P]),
     'gnb_reverse_partial2': (_I, [ctypes.POINTER(GnbGraph), _I, _P, _L, _P, _L, _L, _P, _P]),
     'gnb_score_forward_tc2': (_I, [ctypes.POINTER(GnbGraph), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

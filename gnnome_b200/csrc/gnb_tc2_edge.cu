@@ -47,6 +47,7 @@
 //   ofull[4]      the group's warps (e' in the output buffer)    -> store thread
 //   oempty[4]     store thread (buffer read by the TMA engine)    -> the group's warps
 // Every wait is bounded by the spin watchdog (gnb_tc.cuh): a lost phase traps with a record instead of spinning.
+#include <cstdlib>
 #include <type_traits>
 
 #include "gnb_tma.cuh"
@@ -63,6 +64,14 @@ constexpr int kE2FirstEpiWarp = 4;
 constexpr int kE2Threads = 32 * (kE2FirstEpiWarp + 4 * kE2Groups);
 constexpr int kE2IdxInts = 2 * kE2NT + 4;   // src[32], dst[32], prev_dst, next_dst (+ pad)
 constexpr int kE2IdxSlots = 2;              // index slots per group (see ifull above)
+// L2 management of the launch (gnb_debug_edge_mode; the default is what measured best, profiles/r02i):
+enum EdgeMode : int {
+  kEmLoadEvictFirst = 1,    // TMA loads of the e tiles carry an evict-first policy
+  kEmStoreEvictFirst = 2,   // TMA stores of the e' tiles carry an evict-first policy
+  kEmPrefetchLate = 4,      // the node rows of a tile are prefetched into L2 when its stage is free, not before
+  kEmNoPrefetch = 8,        // no L2 prefetch of the node rows
+  kEmDefault = kEmNoPrefetch,
+};
 
 template <int H>
 struct Edge2Cfg {
@@ -162,7 +171,7 @@ template <int H, bool kResidual, bool kTiming>
 __global__ void __launch_bounds__(kE2Threads, 1)
 edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g, const float* __restrict__ P, int64_t ldP, const __half* __restrict__ Wp,
                         float* __restrict__ F, float* __restrict__ carry, int flags, int workers,
-                        unsigned long long* timing, const Watch watch, int store_delay_ns) {
+                        unsigned long long* timing, const Watch watch, int store_delay_ns, int mode) {
   using C = Edge2Cfg<H>;
   using T = typename C::T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -263,6 +272,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (worker + (int64_t)k * workers < num_tiles) load_idx(worker + (int64_t)k * workers, ring[k]);
     }
     const int64_t ahead = (int64_t)kIdxAhead * workers;
+    const uint64_t l2_stream = l2_policy_evict_first();
     bool more = worker < num_tiles;
     unsigned long long ptm[2] = {0, 0};   // kTiming: cycles waiting for an empty stage, tiles
     for (int i0 = 0; more; i0 += kIdxAhead) {
@@ -272,21 +282,36 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
         const int64_t t = worker + (int64_t)i * workers;
         if (t >= num_tiles) { more = false; break; }
         const int s = k % C::NB;
-        prefetch_rows(ring[k]);
+        if (!(mode & (kEmPrefetchLate | kEmNoPrefetch))) prefetch_rows(ring[k]);
         const long long p0 = kTiming ? clock64() : 0;
         mbar_wait(&empty[s], ((i / C::NB) & 1) ^ 1, 64, watch, watch_tag(kWkEdge2, kWrProducer, kWbEmpty), s, i);
         if (kTiming) { ptm[0] += clock64() - p0; ptm[1] += 1; }
+        if ((mode & kEmPrefetchLate) && !(mode & kEmNoPrefetch)) prefetch_rows(ring[k]);
         if (elect_one()) {
           uint8_t* stage = bufs + (size_t)s * T::BUF_BYTES;
           mbar_arrive_expect_tx(&full[s], T::BUF_BYTES);
+          if (mode & kEmLoadEvictFirst) {
 #pragma unroll
-          for (int kb = 0; kb < T::KBLOCKS; ++kb) {
-            if (C::MC) {   // rank 0 brings the hi halves, rank 1 the lo halves, for both CTAs
-              tma_load_2d_mc(stage + half * T::IMG_BYTES + kb * T::KB_BYTES, &map_e, half * H + kb * kKB, (int)(t * kE2NT),
-                             &full[s], (uint16_t)3);
-            } else {
-              tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s]);
-              tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s]);
+            for (int kb = 0; kb < T::KBLOCKS; ++kb) {
+              if (C::MC) {
+                tma_load_2d_mc_hint(stage + half * T::IMG_BYTES + kb * T::KB_BYTES, &map_e, half * H + kb * kKB,
+                                    (int)(t * kE2NT), &full[s], (uint16_t)3, l2_stream);
+              } else {
+                tma_load_2d_hint(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s], l2_stream);
+                tma_load_2d_hint(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s],
+                                 l2_stream);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int kb = 0; kb < T::KBLOCKS; ++kb) {
+              if (C::MC) {   // rank 0 brings the hi halves, rank 1 the lo halves, for both CTAs
+                tma_load_2d_mc(stage + half * T::IMG_BYTES + kb * T::KB_BYTES, &map_e, half * H + kb * kKB, (int)(t * kE2NT),
+                               &full[s], (uint16_t)3);
+              } else {
+                tma_load_2d(stage + kb * T::KB_BYTES, &map_e, kb * kKB, (int)(t * kE2NT), &full[s]);
+                tma_load_2d(stage + T::IMG_BYTES + kb * T::KB_BYTES, &map_e, H + kb * kKB, (int)(t * kE2NT), &full[s]);
+              }
             }
           }
         }
@@ -349,6 +374,7 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
     if (lane == 0) {
       constexpr int kPer = kE2Groups;
       const int g0 = 0;
+      const uint64_t l2_stream = l2_policy_evict_first();
       int it[kPer];                                        // next tile iteration of each served group
 #pragma unroll
       for (int k = 0; k < kPer; ++k) it[k] = g0 + k;
@@ -369,11 +395,20 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
           if (!mbar_poll(&ofull[grp], (i / kE2Groups) & 1)) continue;
           const int64_t t = worker + (int64_t)i * workers;
           const uint8_t* ob = obufs + (size_t)grp * C::OBUF_BYTES;
+          if (mode & kEmStoreEvictFirst) {
 #pragma unroll
-          for (int kbl = 0; kbl < C::OKB; ++kbl) {
-            const int kb = half * C::OKB + kbl;
-            tma_store_2d(&map_e, ob + kbl * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
-            tma_store_2d(&map_e, ob + C::OIMG_BYTES + kbl * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT));
+            for (int kbl = 0; kbl < C::OKB; ++kbl) {
+              const int kb = half * C::OKB + kbl;
+              tma_store_2d_hint(&map_e, ob + kbl * T::KB_BYTES, kb * kKB, (int)(t * kE2NT), l2_stream);
+              tma_store_2d_hint(&map_e, ob + C::OIMG_BYTES + kbl * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT), l2_stream);
+            }
+          } else {
+#pragma unroll
+            for (int kbl = 0; kbl < C::OKB; ++kbl) {
+              const int kb = half * C::OKB + kbl;
+              tma_store_2d(&map_e, ob + kbl * T::KB_BYTES, kb * kKB, (int)(t * kE2NT));
+              tma_store_2d(&map_e, ob + C::OIMG_BYTES + kbl * T::KB_BYTES, H + kb * kKB, (int)(t * kE2NT));
+            }
           }
           tma_store_commit();
           tma_store_wait_read();
@@ -598,6 +633,15 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
 static unsigned long long* g_edge_timing = nullptr;
 // fault injection: stall the store thread this long after every tile (the schedule must tolerate a slow store thread)
 static int g_store_delay_ns = 0;
+// L2 management (EdgeMode bits): gnb_debug_edge_mode, or GNB_EDGE_MODE in the environment at the first launch
+static int g_edge_mode = -1;
+static int edge_mode() {
+  if (g_edge_mode < 0) {
+    const char* env = getenv("GNB_EDGE_MODE");
+    g_edge_mode = env ? atoi(env) : kEmDefault;
+  }
+  return g_edge_mode;
+}
 
 template <int H>
 static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t ldP, const void* Wp,
@@ -631,7 +675,7 @@ static int edge_forward_tc2_impl(const gnb_graph_t* g, const float* P, int64_t l
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   err = cudaLaunchKernelEx(&cfg, kern, map_e, *g, P, ldP, (const __half*)Wp, F, carry, flags, workers,
-                           g_edge_timing, watch_get(), g_store_delay_ns);
+                           g_edge_timing, watch_get(), g_store_delay_ns, edge_mode());
   if (err != cudaSuccess) {
     set_error("gnb_edge_forward_tc2: launch failed: %s", cudaGetErrorString(err));
     return (int)err;
@@ -651,6 +695,8 @@ extern "C" int gnb_edge_chunk_tc2(int H) { return (H == 64 || H == 128 || H == 2
 extern "C" void gnb_debug_edge_timing(void* buf) { tc::g_edge_timing = (unsigned long long*)buf; }
 
 extern "C" void gnb_debug_store_delay_ns(int ns) { tc::g_store_delay_ns = ns; }
+
+extern "C" void gnb_debug_edge_mode(int mode) { tc::g_edge_mode = mode < 0 ? tc::kEmDefault : mode; }
 
 extern "C" int gnb_edge_forward_tc2(const gnb_graph_t* g, int H, const float* P, int64_t ldP, const void* Wp,
                                     void* e16, float* F, float* carry, int flags, void* stream) {

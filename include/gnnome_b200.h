@@ -216,6 +216,13 @@ void gnb_debug_edge_timing(void* buf);
  * launch failure with a record (run it in a throw-away process: the CUDA context does not survive the trap). */
 void gnb_debug_store_delay_ns(int ns);
 
+/* L2 management of gnb_edge_forward_tc2, a bit mask: 1 = the TMA loads of the e tiles carry an evict-first policy,
+ * 2 = the TMA stores of e' do, 4 = the node rows of a tile are prefetched into L2 when its input stage is free instead
+ * of a tile period earlier, 8 = no prefetch; a negative value restores the library's default (8: what measured best at
+ * BASELINE config 3; GNB_EDGE_MODE in the environment sets it at the first launch).  Results
+ * do not depend on it; tools/edge_modes.py compares the settings. */
+void gnb_debug_edge_mode(int mode);
+
 /* gnb_node_update with e' read from split16 images; writes h' of the nodes node_begin .. node_end as fp32 rows
  * (h_out, row i) and, if h16_out is not NULL, as split16 images (h16_out, row i as well: both outputs are indexed
  * by the absolute node id) for the next layer's gnb_node_linear_tc2 (gated_gcn_full.py:117-137). */

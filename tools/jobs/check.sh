@@ -6,9 +6,11 @@
 #   bench[:WL]       bench.py --workload WL (default cfg3) -> gpurun_out/bench_WL.json + a one-line summary
 #   benchq[:WL]      the same without the CPU legs (kernel work only; -> gpurun_out/benchq_WL.json)
 #   edgetime[:H]     tools/edge_timing.py: cycle accounting of the aggregation kernel's epilogue warps
+#   modes[:WL:REPS]  tools/edge_modes.py: launch time of the aggregation kernel under each L2 management setting
 #   ref              bench.py --impl reference
 #   stress[:WL:N:P]  P fresh processes x N forwards of workload WL (tools/stress.py), default cfg3:100:3
 #   dist:N[:WL]      tools/dist_check.py (inference + training equivalence) + bench.py --workload WL (default cfg3) under torchrun on N GPUs
+#   distbench:N:WL[:TAG]  only the bench of WL under torchrun on N GPUs (-> gpurun_out/bench_WL_xN[TAG].json)
 #   sanitize[:TOOL]  compute-sanitizer --tool TOOL (default synccheck) over the small liveness / parity tests
 cd "${GRAFT_REPO_ROOT:-.}" || exit 1
 mkdir -p gpurun_out
@@ -41,6 +43,7 @@ for st in "${steps[@]}"; do
     benchq) wl=${a1:-cfg3}; timeout 600 python bench.py --workload "$wl" --steps 5 --warmup 3 --no-cpu > "gpurun_out/benchq_$wl.json" 2> "gpurun_out/benchq_$wl.err"
            echo "benchq $wl rc=$?"; summ "gpurun_out/benchq_$wl.json" ;;
     edgetime) timeout 300 python tools/edge_timing.py ${a1:-256} > "gpurun_out/edge_timing_${a1:-256}.txt" 2>&1; grep -v "CTA 0" "gpurun_out/edge_timing_${a1:-256}.txt" | tail -9 ;;
+    modes) timeout 600 python tools/edge_modes.py ${a1:-cfg3} ${a2:-24} ${a3:-} > "gpurun_out/edge_modes_${a1:-cfg3}.txt" 2>&1; tail -10 "gpurun_out/edge_modes_${a1:-cfg3}.txt" ;;
     power) timeout 600 python tools/power_probe.py ${a1:-cfg3} ${a2:-3} > "gpurun_out/power_${a1:-cfg3}.txt" 2>&1; tail -5 "gpurun_out/power_${a1:-cfg3}.txt" ;;
     trywait) timeout 120 tools/microbench/trywait_probe > gpurun_out/trywait_probe.txt 2>&1; cat gpurun_out/trywait_probe.txt ;;
     ref)   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.json ;;
@@ -50,6 +53,8 @@ for st in "${steps[@]}"; do
            timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py > "gpurun_out/dist_check_x$n.log" 2>&1; echo "dist_check x$n rc=$?"; tail -4 "gpurun_out/dist_check_x$n.log"
            wl=${a2:-cfg3}
            timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus "$n" --workload "$wl" --steps 5 --warmup 3 > "gpurun_out/bench_${wl}_x$n.json" 2> "gpurun_out/bench_${wl}_x$n.err"; echo "bench $wl x$n rc=$?"; summ "gpurun_out/bench_${wl}_x$n.json" ;;
+    distbench) n=${a1:-2}; wl=${a2:-cfg3}; tag=${a3:-}
+           timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus "$n" --workload "$wl" --steps 5 --warmup 3 > "gpurun_out/bench_${wl}_x$n$tag.json" 2> "gpurun_out/bench_${wl}_x$n$tag.err"; echo "bench $wl x$n $tag rc=$?"; summ "gpurun_out/bench_${wl}_x$n$tag.json" ;;
     sanitize) tool=${a1:-synccheck}
            timeout 1500 compute-sanitizer --tool "$tool" python -m pytest tests/test_gpu_liveness.py -q -x -k "stalled and 3000" > "gpurun_out/sanitize_$tool.log" 2>&1; echo "sanitize $tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed" "gpurun_out/sanitize_$tool.log" | tail -3 ;;
     *) echo "unknown step $st" ;;

@@ -12,6 +12,7 @@ from gnnome_b200.layers.encoders import encode_rows2
 
 wl = sys.argv[1] if len(sys.argv) > 1 else 'cfg3'
 secs = float(sys.argv[2]) if len(sys.argv) > 2 else 3.0
+only = sys.argv[3].split(',') if len(sys.argv) > 3 else None   # substrings of the kernel names to probe
 n, m, H, L, _ = bench.WORKLOADS[wl]
 dev = torch.device('cuda', 0)
 model = bench.make_model(H, L, dev)
@@ -54,6 +55,8 @@ with torch.no_grad():
     print(f'{wl}: N={n} E={m} H={H}; max SM clock {pynvml.nvmlDeviceGetMaxClockInfo(nv, pynvml.NVML_CLOCK_SM)} MHz, '
           f'power limit {pynvml.nvmlDeviceGetPowerManagementLimit(nv) / 1000:.0f} W')
     for name, fn in kernels.items():
+        if only and not any(o in name for o in only):
+            continue
         fn(); torch.cuda.synchronize()
         time.sleep(1.0)                                   # let the board cool down to idle power
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
