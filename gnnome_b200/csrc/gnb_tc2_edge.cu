@@ -15,8 +15,8 @@
 // TMEM, and walks 32-edge tiles of the dst-sorted edge array.  Tile i of a CTA belongs to epilogue group i % 4.
 //
 //   warp 0      : producer.  TMA loads of the tile's operand images into input stage i % NB (the loads run NB tiles
-//                 ahead of the tensor core), the tile's (src, dst) indices into the group's index slot, L2 prefetch
-//                 of the node rows the epilogue will gather.
+//                 ahead of the tensor core), the tile's (src, dst) indices into the group's index slot; optionally
+//                 (EdgeMode, off by default) an L2 prefetch of the node rows the epilogue will gather.
 //   warps 1, 3  : MMA issue (one lane each; warp 1 the even tiles of the CTA, warp 3 the odd ones): 3 K/16 split products
 //                 into the group's accumulator set + 2 HC/16 identity products for the residual, descriptors advanced
 //                 from one base per tile; the commit RELEASES THE INPUT STAGE -- nothing but the tensor core
@@ -246,9 +246,12 @@ edge_forward_tc2_kernel(const __grid_constant__ CUtensorMap map_e, gnb_graph_t g
       if (lane == 0 && t > 0) r[2] = g.in_dst[t * kE2NT - 1];
       if (lane == 1 && (t + 1) * kE2NT < E) r[2] = g.in_dst[(t + 1) * kE2NT];
     };
-    // Every node row is touched for the first time by SOME gather of the epilogue, and that one would wait for
-    // HBM; the producer knows the tile's endpoints NB tile periods before the epilogue needs them, so it pulls
-    // this CTA's slices of the (B1h, A2h)[src] and B2h[dst] rows into L2 ahead of time.
+    // Every node row is touched for the first time by SOME gather of the epilogue, and that one waits for HBM; the
+    // producer knows the tile's endpoints NB tile periods before the epilogue needs them and can pull this CTA's slices
+    // of the (B1h, A2h)[src] and B2h[dst] rows into L2 ahead of time.  OFF by default (kEmNoPrefetch): at config 3 a
+    // line lives ~12 us in the L2, about the distance between this prefetch and its use, so rows were read from DRAM
+    // twice (150 GB per launch instead of 94 GB, 45.2 ms instead of 40.2 ms: profiles/r02i); the three quads of
+    // gathers each epilogue warp keeps in flight cover the first-touch latency instead.
     auto prefetch_rows = [&](const int (&r)[3]) {
       const char* a = reinterpret_cast<const char*>(P + (int64_t)r[0] * ldP + 2 * half * C::HC);
 #pragma unroll

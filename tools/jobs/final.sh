@@ -1,4 +1,4 @@
-bash tools/jobs/check.sh smoke tests bench:cfg3 ref bench:cfg2 sanitize
-bash tools/jobs/profile.sh cfg3 launches metrics:edge_forward_tc2
-bash tools/jobs/profile.sh mid full:edge_forward_tc2
-bash tools/jobs/check.sh stress:cfg3:80:4
+# the verification pass behind the round's closing numbers (profiles/r02j_*)
+bash tools/jobs/check.sh smoke tests bench:cfg3 ref bench:cfg2
+bash tools/jobs/profile.sh cfg3 launches
+bash tools/jobs/check.sh stress:cfg3:60:2
