@@ -308,7 +308,7 @@ def run_reference_arm(args, wl):
     line = {
         'impl': 'reference', 'metric': 'edges/s', 'value': value, 'unit': 'edges/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': t * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': desc, 'N': n, 'E': m, 'H': H, 'L': L, 'sample': sample},
         'cpu_baseline': {'value': value, 'unit': 'edges/s', 'cores': r['cores'], 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'edges/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -501,7 +501,7 @@ def run_gpu_arm(args, wl):
 
     line = {
         'metric': 'edges/s', 'value': value, 'unit': 'edges/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong' if world > 1 else 'weak',
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32 (state held as split fp16 hi+lo pairs, 22 significant bits; fp16x2-split tcgen05 products, f32 accumulate)', 'data': 'synthetic',
         'config': {'workload': desc, 'N': n, 'E': m, 'H': H, 'L': L, 'model': 'SymGatedGCNModel eval, seed-0 init',
                    'graph': 'make_assembly_graph(seed=0, band=64, alpha=2.2, p_long=0.01)',

@@ -76,11 +76,8 @@ class GatedGCNModel(nn.Module):
             e16, _ = encode_rows2(e_d, gi.in_eid, ee.linear1, ee.linear2, gi.E)
             h32, h16, e16 = self.gnn.forward_positions16(gi, h32, h16, e16)
             return self.predictor.score_positions16(gi, self.predictor.node_rows16(h16), e16).to(out_dev)
-        h = encode_rows(x_d, None, self.node_encoder.linear1, self.node_encoder.linear2, gi.N)
-        if self.directed:                                                                  # :45-46
-            e_pos = encode_rows(e_d, gi.in_eid, self.edge_encoder.linear1, self.edge_encoder.linear2, gi.E)
-            h, e_pos = self.gnn.forward_positions(gi, h, e_pos)
-        else:
+        gi2 = None
+        if not self.directed:
             # dgl.add_reverse_edges (:48): edge ids [0,E) = originals, [E,2E) = reversed copies that
             # carry the same input features (:49).  The doubled graph gets its own index.
             gi2 = getattr(gi, '_undirected', None)
@@ -91,6 +88,23 @@ class GatedGCNModel(nn.Module):
                 inv = torch.empty(gi2.E, dtype=torch.int64, device=gi.device)
                 inv[gi2.in_eid[:gi2.E].long()] = torch.arange(gi2.E, device=gi.device)
                 gi2._orig_rows = inv[gi.in_eid[:gi.E].long()].to(torch.int32).contiguous()
+            if state_format(self.node_encoder.linear2.out_features) == 'split16' and gi.E > 0:
+                # the same wiring on the split16 / tcgen05 kernels: the edge state of the doubled graph as fp16 (hi, lo)
+                # images, the rows of the original edges (:51 e[:E]) gathered as 4-byte words in gi's position order
+                from .. import ops
+                ne, ee = self.node_encoder, self.edge_encoder
+                H = ne.linear2.out_features
+                h16, h32 = encode_rows2(x_d, None, ne.linear1, ne.linear2, gi.N, want32=True)
+                e16 = encode_rows2(e_d, gi2._feat_idx, ee.linear1, ee.linear2, gi2.E)[0]
+                h32, h16, e16 = self.gnn.forward_positions16(gi2, h32, h16, e16)
+                words = ops.gather_rows(e16.view(gi2.E, -1).view(torch.float32), gi2._orig_rows)
+                e16o = words.view(torch.float16).view(gi.E, 2, H)
+                return self.predictor.score_positions16(gi, self.predictor.node_rows16(h16), e16o).to(out_dev)
+        h = encode_rows(x_d, None, self.node_encoder.linear1, self.node_encoder.linear2, gi.N)
+        if self.directed:                                                                  # :45-46
+            e_pos = encode_rows(e_d, gi.in_eid, self.edge_encoder.linear1, self.edge_encoder.linear2, gi.E)
+            h, e_pos = self.gnn.forward_positions(gi, h, e_pos)
+        else:
             e2 = encode_rows(e_d, gi2._feat_idx, self.edge_encoder.linear1, self.edge_encoder.linear2, gi2.E)
             h, e2 = self.gnn.forward_positions(gi2, h, e2)
             from .. import ops

@@ -231,6 +231,30 @@ def test_other_models_vs_reference_golden(gnb, golden, name, ctor):
     assert (out.cpu() - g['logits']).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize('H,L', [(64, 3), (128, 2), (256, 2)])
+def test_undirected_model_on_the_split16_path(gnb, H, L):
+    """GatedGCNModel(directed=False) (models/full_graph.py:47-52: add_reverse_edges, e = cat(e, e), e[:E]) at the widths
+    of the tcgen05 kernels: the doubled graph runs on the split16 path and the original edges' rows are picked out of
+    the fp16 (hi, lo) images.  Against the oracle and against the CUDA-core fp32 kernels (the path the reference's
+    hidden-32 fixture exercises, test_other_models_vs_reference_golden)."""
+    src, dst, n, x, e = _graph(5000, 30000, seed=H + 1)
+    sd = R.init_state_dict(model='gated', hidden=H, num_layers=L, seed=H)
+    model = gnb.models.GatedGCNModel(2, 2, H, 16, L, 64, 'batch', directed=False)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        out = model((src, dst, n), x.cuda(), e.cuda())
+        ref = R.model_forward(sd, src, dst, n, x, e, model='gated', directed=False)
+        gnb.set_backend('ffma')
+        try:
+            out32 = model((src, dst, n), x.cuda(), e.cuda())
+        finally:
+            gnb.set_backend('tc2')
+    assert out.shape == (src.numel(), 1) and out.is_cuda
+    assert _prob_err(out, ref) <= PROB_TOL
+    assert _prob_err(out, out32) <= 2e-5
+
+
 @pytest.mark.parametrize('H,L,n,m', [(64, 8, 20000, 120000), (128, 4, 10000, 60000), (256, 3, 6000, 36000)])
 def test_model_vs_oracle_fp64(gnb, backend, shipped_weights, H, L, n, m):
     """Against the fp64 evaluation of the oracle ("true value"): our error must stay within the
