@@ -280,7 +280,7 @@ class ShardedForward:
     """``SymGatedGCNModel`` / ``GatedGCNModel(directed=True)`` forward (eval) on this rank's shard.
 
     ``step()`` returns the (E_own, 1) logits of the owned edges, ordered like ``owned_edge_ids``
-    (ascending global DGL edge ids).  Inputs are the GLOBAL graph / features (every rank passes the
+    (ascending global DGL edge ids).  ``GatedGCNModel(directed=False)`` is sharded over its doubled graph.  Inputs are the GLOBAL graph / features (every rank passes the
     same); only the shard is kept on the device."""
 
     def __init__(self, model, src, dst, num_nodes, x, e, rank, world, device, kernels=None, group=None,
@@ -291,18 +291,28 @@ class ShardedForward:
         if model.training:
             raise NotImplementedError('ShardedForward runs eval mode')
         self.sym = hasattr(model, 'linear1_node')
-        if not self.sym and not getattr(model, 'directed', True):
-            raise NotImplementedError('GatedGCNModel(directed=False) is not sharded')
         src, dst = torch.as_tensor(src), torch.as_tensor(dst)
         if torch.device(device).type == 'cuda':          # build the index tables on the GPU (sort / unique of E ids)
             src, dst = src.to(device), dst.to(device)
+        # GatedGCNModel(directed=False), models/full_graph.py:47-52: the layers run on the graph with every edge doubled
+        # by its reverse (ids [E, 2E), same input features) and the predictor scores the original edges.  Here the
+        # DOUBLED graph is what gets partitioned; a rank scores every edge it owns and returns the original ones.
+        self.undirected = not self.sym and not getattr(model, 'directed', True)
+        self.num_edges_orig = int(src.numel())
+        if self.undirected:
+            src, dst = torch.cat((src, dst)), torch.cat((dst, src))
         self.shard = sh = Shard(src, dst, num_nodes, rank, world)
         self.plan = HaloPlan(sh, device, group, comm)
         self.owned_edge_ids = sh.edge_ids
+        self._keep = None
+        if self.undirected:
+            self._keep = torch.nonzero(sh.edge_ids < self.num_edges_orig).squeeze(1).to(device)
+            self.owned_edge_ids = sh.edge_ids[self._keep.to(sh.edge_ids.device)]
         self.gi = self.k.stage(sh.src_local.to(device), sh.dst_local.to(device), sh.n_local)
         self.x_own = torch.as_tensor(x)[sh.lo:sh.hi].to(device=device, dtype=dtype).contiguous()
         e = torch.as_tensor(e)
-        self.e_own = e[sh.edge_ids.to(e.device)].to(device=device, dtype=dtype).contiguous()
+        feat_ids = sh.edge_ids % max(self.num_edges_orig, 1) if self.undirected else sh.edge_ids   # :49 e = cat(e, e)
+        self.e_own = e[feat_ids.to(e.device)].to(device=device, dtype=dtype).contiguous()
         del src, dst
         self._host = None
         self.ws = {}
@@ -378,7 +388,7 @@ class ShardedForward:
             S[n_own:, :hs].copy_(plan.to_consumers(out_rows, self._buf('r3', (n_halo, hs))))
         scores = torch.empty((sh.num_edges, 1), dtype=self.dtype, device=self.device)
         k.score_forward(m.predictor, gi, S, e_pos, scores)
-        return scores
+        return scores if self._keep is None else scores[self._keep]
 
     def step(self):
         return self.forward(self.gi, self.x_own, self.e_own)
@@ -388,7 +398,7 @@ class ShardedForward:
         sh = self.shard
         pin = lambda t: t.cpu().contiguous().pin_memory()
         self._host = dict(src=pin(sh.src_local), dst=pin(sh.dst_local), x=pin(self.x_own), e=pin(self.e_own),
-                          out=torch.empty((sh.num_edges, 1), dtype=torch.float32).pin_memory())
+                          out=torch.empty((int(self.owned_edge_ids.numel()), 1), dtype=torch.float32).pin_memory())
         return sum(self._host[n].numel() * self._host[n].element_size() for n in ('src', 'dst', 'x', 'e')), \
             self._host['out'].numel() * 4
 

@@ -128,3 +128,26 @@ def test_overlapped_schedule_is_bit_identical_to_the_serial_one(world, H, p_long
     b, _ = _run_sharded(gnb, model, src, dst, n, x, e, world, overlap=False)
     assert sum(i[3] for i in info) > 0
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('world,H', [(3, 64), (4, 128)])
+def test_undirected_model_sharded_over_its_doubled_graph(world, H):
+    """GatedGCNModel(directed=False): the graph with every edge doubled by its reverse is what gets partitioned; each
+    rank scores the edges it owns and returns the original ones (models/full_graph.py:47-52)."""
+    import gnnome_b200 as gnb
+    n, m, L = 9_000, 54_000, 2
+    src, dst = synth.make_assembly_graph(n, m, seed=11, p_long=0.1)
+    x, e = synth.make_features(src, dst, n, seed=11)
+    src, dst, x, e = map(torch.from_numpy, (src, dst, x, e))
+    sd = R.init_state_dict(model='gated', hidden=H, num_layers=L, seed=H)
+    model = gnb.models.GatedGCNModel(2, 2, H, 16, L, 64, 'batch', directed=False)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        single = model((src, dst, n), x.cuda(), e.cuda())
+    sharded, info = _run_sharded(gnb, model, src, dst, n, x, e, world)
+    assert sum(i[0] for i in info) == n and sum(i[2] for i in info) == 2 * m     # the doubled graph is what is split
+    prob = lambda t: torch.sigmoid(t.double().cpu())  # noqa: E731
+    assert (prob(sharded) - prob(single)).abs().max().item() <= 1e-5
+    ref = R.model_forward(sd, src, dst, n, x, e, model='gated', directed=False)
+    assert (prob(sharded) - prob(ref)).abs().max().item() <= 1e-4

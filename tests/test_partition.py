@@ -41,7 +41,7 @@ def _worker(rank, world, port, kind, n, m, p_long, out_path):
         if kind == 'sym':
             model = gnnome_b200.models.SymGatedGCNModel(2, 2, 32, 16, 3, 64, 'batch')
         else:
-            model = gnnome_b200.models.GatedGCNModel(2, 2, 32, 16, 3, 64, 'batch', directed=True)
+            model = gnnome_b200.models.GatedGCNModel(2, 2, 32, 16, 3, 64, 'batch', directed=(kind != 'gated_undirected'))
         with torch.no_grad():
             for mod in model.modules():                      # non-trivial eval-mode BatchNorm statistics
                 if isinstance(mod, torch.nn.BatchNorm1d):
@@ -56,18 +56,19 @@ def _worker(rank, world, port, kind, n, m, p_long, out_path):
             local = runner.step()
             full = partition.gather_scores(runner, local, m)
         sizes = [None] * world
-        dist.all_gather_object(sizes, (runner.shard.n_own, runner.shard.n_halo, runner.shard.num_edges))
+        dist.all_gather_object(sizes, (runner.shard.n_own, runner.shard.n_halo, int(runner.owned_edge_ids.numel())))
         if rank == 0:
             sd = {k: v.clone() for k, v in model.state_dict().items()}
             ref = R.model_forward(sd, src, dst, n, x, e, model='sym' if kind == 'sym' else 'gated',
-                                  dtype=torch.float64, faithful=False)
+                                  directed=(kind != 'gated_undirected'), dtype=torch.float64, faithful=False)
             err = (full.double() - ref).abs().max().item()
             torch.save({'err': err, 'sizes': sizes}, out_path)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,kind,p_long', [(2, 'sym', 0.01), (3, 'sym', 0.3), (2, 'gated', 0.05)])
+@pytest.mark.parametrize('world,kind,p_long', [(2, 'sym', 0.01), (3, 'sym', 0.3), (2, 'gated', 0.05),
+                                                  (3, 'gated_undirected', 0.05)])
 def test_sharded_forward_matches_oracle_gloo(tmp_path, world, kind, p_long):
     n, m = 600, 3600
     out = str(tmp_path / 'res.pt')
