@@ -67,6 +67,9 @@ class GatedGCNModel(nn.Module):
         if self.directed and (self.training or self.gnn.convs[0].normalization == 'layer'):
             from ..autograd import model_forward
             return model_forward(self, graph, x, e)
+        if self.training:
+            raise NotImplementedError('training GatedGCNModel(directed=False) runs through gnnome_b200.train_dist.ShardedTrainer '
+                                      '(one rank is enough on one GPU); model(graph, x, e) covers eval mode')
         gi = GraphIndex.from_graph(graph)
         out_dev = x.device
         x_d, e_d = _to_dev(x, gi.device), _to_dev(e, gi.device)

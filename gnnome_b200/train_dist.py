@@ -210,7 +210,7 @@ class CudaPrims:
 # the sharded training step
 # ------------------------------------------------------------------------------------------------
 class ShardedTrainer:
-    """``SymGatedGCNModel`` / ``GatedGCNModel(directed=True)`` in ``model.train()`` mode on this rank's shard.
+    """``SymGatedGCNModel`` / ``GatedGCNModel`` (directed or not) in ``model.train()`` mode on this rank's shard.
 
     ``src, dst, x, e, y`` are the GLOBAL graph, features and edge labels (every rank passes the same; only the shard is
     kept on the device).  ``step(optimizer)`` runs forward, loss, backward, the gradient all-reduce and the optimiser
@@ -225,25 +225,33 @@ class ShardedTrainer:
         self.dtype, self.checkpoint = dtype, checkpoint
         self.p = prims if prims is not None else CudaPrims(self.device)
         self.sym = hasattr(model, 'linear1_node')
-        if not self.sym and not getattr(model, 'directed', True):
-            raise NotImplementedError('GatedGCNModel(directed=False) is not sharded')
         if any(prm.device != self.device for prm in model.parameters()):
             raise RuntimeError(f'sharded training needs the model on {self.device}: call model.to(device) first')
         src, dst = torch.as_tensor(src), torch.as_tensor(dst)
         if self.device.type == 'cuda':
             src, dst = src.to(self.device), dst.to(self.device)
+        # GatedGCNModel(directed=False), models/full_graph.py:47-52: the layers (and their edge BatchNorm statistics) run
+        # on the graph with every edge doubled by its reverse (ids [E, 2E), the same encoded features, :49), the
+        # predictor and the loss see the original edges (:51-52).  The DOUBLED graph is what gets partitioned; the
+        # reversed copies an owner holds are scored too and carry weight 0 in the loss.
+        self.undirected = not self.sym and not getattr(model, 'directed', True)
+        e_orig = int(src.numel())
+        if self.undirected:
+            src, dst = torch.cat((src, dst)), torch.cat((dst, src))
         self.shard = sh = Shard(src, dst, num_nodes, rank, world)
         self.plan = HaloPlan(sh, self.device, group)
         self.ex = _Exchange(sh, self.plan)
-        self.n_global, self.e_global = int(num_nodes), int(src.numel())
+        self.n_global, self.e_global, self.e_loss = int(num_nodes), int(src.numel()), e_orig
         self.gi = self.p.stage(sh.src_local.to(self.device), sh.dst_local.to(self.device), sh.n_local)
         order = self.p.position_eids(self.gi)                          # local edge id at every dst-sorted position
         self.order = order
         ids = sh.edge_ids
-        pick = lambda t: torch.as_tensor(t)[ids.to(torch.as_tensor(t).device)].to(device=self.device, dtype=dtype)  # noqa: E731
+        feat = ids % max(e_orig, 1) if self.undirected else ids
+        pick = lambda t: torch.as_tensor(t)[feat.to(torch.as_tensor(t).device)].to(device=self.device, dtype=dtype)  # noqa: E731
         self.x_own = torch.as_tensor(x)[sh.lo:sh.hi].to(device=self.device, dtype=dtype).contiguous()
         self.e_pos = pick(e)[order].contiguous()                       # edge rows in position order from here on
         self.y_pos = pick(y)[order].contiguous()
+        self.w_pos = (ids < e_orig).to(device=self.device, dtype=dtype)[order].contiguous() if self.undirected else None
         self.pos_weight = None if pos_weight is None else torch.as_tensor(pos_weight, dtype=dtype, device=self.device)
         self.owned_edge_ids = ids
 
@@ -325,8 +333,8 @@ class ShardedTrainer:
 
     def loss(self, scores_pos):
         """train.py:143-144: mean BCE-with-logits over ALL edges; this rank's share (the shares add up to the loss)."""
-        return F.binary_cross_entropy_with_logits(scores_pos.squeeze(-1), self.y_pos, pos_weight=self.pos_weight,
-                                                  reduction='sum') / self.e_global
+        return F.binary_cross_entropy_with_logits(scores_pos.squeeze(-1), self.y_pos, weight=self.w_pos,
+                                                  pos_weight=self.pos_weight, reduction='sum') / self.e_loss
 
     def reduce_gradients(self):
         """Sum the ranks' gradient contributions: one flat all-reduce over every parameter (missing gradients count
@@ -356,5 +364,6 @@ class ShardedTrainer:
         return total
 
     def scores_in_edge_order(self, scores_pos):
-        """(E_own, 1) logits ordered like ``owned_edge_ids`` (ascending global edge ids)."""
+        """(E_own, 1) logits ordered like ``owned_edge_ids`` (ascending global edge ids; for ``directed=False`` models the
+        ids >= E are the reversed copies, whose scores the reference never looks at)."""
         return torch.empty_like(scores_pos).index_copy(0, self.order, scores_pos)

@@ -47,7 +47,7 @@ def _worker(rank, world, port, kind, norm, n, m, p_long, checkpoint, out_path):
         if kind == 'sym':
             model = gnnome_b200.models.SymGatedGCNModel(2, 2, H, 16, L, 64, norm)
         else:
-            model = gnnome_b200.models.GatedGCNModel(2, 2, H, 16, L, 64, norm, directed=True)
+            model = gnnome_b200.models.GatedGCNModel(2, 2, H, 16, L, 64, norm, directed=(kind != 'gated_undirected'))
         model = model.double().train()
         sd = {k: v.clone() for k, v in model.state_dict().items()}
         tr = train_dist.ShardedTrainer(model, src, dst, n, x, e, y, rank, world, torch.device('cpu'), pos_weight=0.4,
@@ -62,7 +62,8 @@ def _worker(rank, world, port, kind, norm, n, m, p_long, checkpoint, out_path):
             # oracle: the same step on one process through the restatement under torch autograd
             p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone())
                  for k, v in sd.items()}
-            ref = R.model_forward(p, src, dst, n, x, e, model=kind, normalization=norm, training=True, cast=False, dtype=torch.float64).squeeze(-1)
+            okind, odir = ('gated', False) if kind == 'gated_undirected' else (kind, True)
+            ref = R.model_forward(p, src, dst, n, x, e, model=okind, directed=odir, normalization=norm, training=True, cast=False, dtype=torch.float64).squeeze(-1)
             ref_loss = F.binary_cross_entropy_with_logits(ref, y, pos_weight=torch.tensor(0.4, dtype=torch.float64))
             ref_loss.backward()
             gerr = {}
@@ -76,7 +77,7 @@ def _worker(rank, world, port, kind, norm, n, m, p_long, checkpoint, out_path):
                 p2 = {k: v.detach().clone() for k, v in p.items()}
                 for k, prm in model.named_parameters():
                     p2[k] = prm.detach().clone()
-                R.model_forward(p2, src, dst, n, x, e, model=kind, normalization=norm, training=True, cast=False, dtype=torch.float64)
+                R.model_forward(p2, src, dst, n, x, e, model=okind, directed=odir, normalization=norm, training=True, cast=False, dtype=torch.float64)
                 for k, b in model.named_buffers():
                     berr[k] = float((b.double() - p2[k].double()).abs().max())
             torch.save({'loss': float(loss), 'ref_loss': float(ref_loss), 'gerr': gerr, 'berr': berr, 'sizes': sizes,
@@ -88,7 +89,7 @@ def _worker(rank, world, port, kind, norm, n, m, p_long, checkpoint, out_path):
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('world,kind,norm,p_long,checkpoint', [
     (2, 'sym', 'batch', 0.05, True), (3, 'sym', 'batch', 0.3, False), (2, 'gated', 'batch', 0.05, True),
-    (2, 'sym', 'layer', 0.1, True)])
+    (2, 'sym', 'layer', 0.1, True), (3, 'gated_undirected', 'batch', 0.1, True)])
 def test_sharded_training_step_matches_oracle_autograd_gloo(tmp_path, world, kind, norm, p_long, checkpoint):
     n, m = 400, 2400
     out = str(tmp_path / 'res.pt')
@@ -100,5 +101,5 @@ def test_sharded_training_step_matches_oracle_autograd_gloo(tmp_path, world, kin
     assert worst <= 1e-8, sorted(res['gerr'].items(), key=lambda kv: -kv[1])[:5]
     if res['berr']:
         assert max(res['berr'].values()) <= 1e-8, sorted(res['berr'].items(), key=lambda kv: -kv[1])[:5]
-    assert sum(s[0] for s in res['sizes']) == n and sum(s[2] for s in res['sizes']) == m
+    assert sum(s[0] for s in res['sizes']) == n and sum(s[2] for s in res['sizes']) == (2 * m if kind == 'gated_undirected' else m)
     assert all(s[1] > 0 for s in res['sizes'])
